@@ -1,0 +1,24 @@
+"""CPU oracle for the implicit-feedback fit() hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``spotlight_b200/`` may import this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker
+or the timed CPU baseline -- never as the product path.
+
+Contents (every function cites the reference file:line it restates):
+
+* ``mt19937``   -- NumPy-legacy ``RandomState`` stream (MT19937 + masked
+                   rejection) that drives ``sample_items`` and ``shuffle``.
+* ``murmur``    -- MurmurHash3_x86_32 as used by ``BloomEmbedding``.
+* ``mf``        -- BilinearNet forward / the four losses / closed-form backward.
+* ``seq``       -- PoolNet and CNNNet forward / backward closed forms.
+* ``torch_port``-- the reference's fit() loop restated on stock torch CPU ops
+                   (the timed ``cpu_baseline`` "port").
+* ``c/``        -- plain-C restatement of the integer parts and the MF step,
+                   compiled by ``__graft_entry__.build()`` into ``oracle/_c``.
+
+Parity pinning: the restatements are checked (tests/test_oracle_*.py) against
+golden vectors produced by the *live* reference in the build container
+(``tests/golden/make_golden.py`` imports ``/root/reference``), against NumPy's
+own ``RandomState`` and against ``sklearn.utils.murmurhash3_32``.
+"""
