@@ -1,0 +1,555 @@
+// Fused implicit-feedback matrix-factorisation training step for sm_100a.
+//
+// Replaces the loop body of ImplicitFactorizationModel.fit
+// (spotlight/factorization/implicit.py:229-242): two BilinearNet forwards
+// (spotlight/factorization/representations.py:80-91), one of
+// pointwise/bpr/hinge/adaptive_hinge (spotlight/losses.py:40-50, 82-90,
+// 115-124, 164-166) and loss.backward() (8x aten::embedding_dense_backward).
+//
+// One kernel per direction:
+//   mf_fwd_kernel  gathers U[u], Q[i+], Q[i-] with 128-bit loads (LPR = D/4
+//                  lanes per row, <=32), warp-shuffle dot, loss, d loss/d score,
+//                  emits rank-1 gradient "terms" (user row, item row, g) and
+//                  counts row occurrences with integer atomics.
+//   mf_bwd_kernel  one lane group per touched row: sums g * partner-row over the
+//                  row's terms in ascending term order (deterministic), writes
+//                  the gradient row once (dense or compact).
+// Between them: seg_scan_kernel + mf_fill_kernel build the inverted index
+// (segindex.cuh).  mf_apply_kernel is the optional fused row-wise optimizer.
+//
+// Algorithmic HBM bytes per interaction (fp32, D = dim, R = 4D):
+//   forward 3R + 3*4 + 3*8, backward re-reads 4R (partner rows), writes <= 3R.
+#include "segindex.cuh"
+
+namespace {
+
+constexpr int MF_THREADS = 256;
+
+struct MfDev {
+    int64_t B;
+    int64_t T;   // number of rank-1 terms (2B for a training step)
+    const int64_t* users; const int64_t* items; const int64_t* negs;
+    int32_t loss; int32_t n_neg;
+    int64_t U, I; int32_t D;
+    float* Wu; float* Wi; float* bu; float* bi;
+    float* loss_out; float* pos_out; float* neg_out;
+    // terms
+    int32_t* t_a; int32_t* t_b; float* t_g;
+    // loss reduction
+    float* partial; int32_t* done;
+    int32_t* err;
+    SegIndex seg;
+    // grads
+    int32_t grad_mode;
+    float* dWu; float* dWi; float* dbu; float* dbi;
+    int64_t* urows; float* gWu; float* gbu;
+    int64_t* irows; float* gWi; float* gbi;
+    int32_t* compact_counts;
+    int32_t opt; float lr, wd, eps;
+    float* sWu; float* sWi; float* sbu; float* sbi;
+};
+
+template <int LPR>
+__device__ __forceinline__ float row_dot(const float* __restrict__ a, const float* __restrict__ b,
+                                         int D, int gl, unsigned gmask) {
+    float acc = 0.f;
+    for (int c = gl * 4; c < D; c += LPR * 4) acc += dot4(ldg4(a + c), ldg4(b + c));
+    return group_sum<LPR>(acc, gmask);
+}
+
+// d loss_b / d pos and d loss_b / d neg (unscaled by 1/B), and the loss term.
+__device__ __forceinline__ void pair_loss(int loss, float p, float n, float& per, float& gp, float& gn) {
+    if (loss == SLB_LOSS_BPR) {
+        const float s = sigmoidf_(p - n);
+        per = 1.0f - s;
+        gp = -s * (1.0f - s);
+        gn = -gp;
+    } else if (loss == SLB_LOSS_POINTWISE) {
+        const float sp = sigmoidf_(p), sn = sigmoidf_(n);
+        per = (1.0f - sp) + sn;
+        gp = -sp * (1.0f - sp);
+        gn = sn * (1.0f - sn);
+    } else {  // hinge / adaptive hinge on the selected negative
+        const float z = n - p + 1.0f;
+        per = fmaxf(z, 0.0f);
+        const float act = z >= 0.0f ? 1.0f : 0.0f;  // clamp backward passes at the boundary
+        gp = -act;
+        gn = act;
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
+    __shared__ float sh_red[MF_THREADS / 32];
+    const int gl = threadIdx.x & (LPR - 1);
+    const unsigned gmask = group_mask(LPR);
+    constexpr int GROUPS = MF_THREADS / LPR;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / LPR;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * GROUPS;
+    const float invB = 1.0f / static_cast<float>(a.B);
+    const int D = a.D;
+    float lsum = 0.f;
+
+    // every group runs the same number of iterations so shuffles stay converged
+    const int64_t iters = (a.B + gstride - 1) / gstride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t b = gid + it * gstride;
+        const bool valid = b < a.B;
+        const int64_t bb = valid ? b : 0;
+        const int64_t u = a.users[bb], i = a.items[bb];
+        bool bad = u < 0 || u >= a.U || i < 0 || i >= a.I;
+        const int64_t uc = bad ? 0 : u, ic = bad ? 0 : i;
+        const float* urow = a.Wu + uc * D;
+        float p, n;
+        int64_t nu, nj;
+        if (a.loss != SLB_LOSS_ADAPTIVE_HINGE) {
+            int64_t j = a.negs[bb];
+            if (j < 0 || j >= a.I) { bad = true; j = 0; }
+            const float* qi = a.Wi + ic * D;
+            const float* qj = a.Wi + j * D;
+            float dp = 0.f, dn = 0.f;
+            for (int c = gl * 4; c < D; c += LPR * 4) {   // one trip for D <= 128
+                const float4 u4 = ldg4(urow + c), i4 = ldg4(qi + c), j4 = ldg4(qj + c);
+                dp += dot4(u4, i4);
+                dn += dot4(u4, j4);
+            }
+            const float ub = __ldg(a.bu + uc);
+            p = group_sum<LPR>(dp, gmask) + ub + __ldg(a.bi + ic);
+            n = group_sum<LPR>(dn, gmask) + ub + __ldg(a.bi + j);
+            nu = uc; nj = j;
+            if (valid && gl == 0 && a.neg_out) a.neg_out[bb] = n;
+        } else {
+            // implicit.py:266-275: flat f = k*B + b is scored with users[f / n_neg]
+            p = row_dot<LPR>(urow, a.Wi + ic * D, D, gl, gmask) + __ldg(a.bu + uc) + __ldg(a.bi + ic);
+            n = -INFINITY; nu = 0; nj = 0;
+            for (int k = 0; k < a.n_neg; ++k) {
+                const int64_t f = static_cast<int64_t>(k) * a.B + bb;
+                int64_t u2 = a.users[f / a.n_neg], j = a.negs[f];
+                if (u2 < 0 || u2 >= a.U || j < 0 || j >= a.I) { bad = true; u2 = 0; j = 0; }
+                const float nk = row_dot<LPR>(a.Wu + u2 * D, a.Wi + j * D, D, gl, gmask) +
+                                 __ldg(a.bu + u2) + __ldg(a.bi + j);
+                if (valid && gl == 0 && a.neg_out) a.neg_out[f] = nk;
+                if (nk > n || k == 0) { n = nk; nu = u2; nj = j; }  // first arg-max
+            }
+        }
+        if (valid && gl == 0) {
+            if (bad) atomicExch(a.err, 1);
+            float per, gp, gn;
+            pair_loss(a.loss, p, n, per, gp, gn);
+            lsum += per;
+            gp *= invB; gn *= invB;
+            if (bad) { gp = 0.f; gn = 0.f; }
+            if (a.pos_out) a.pos_out[bb] = p;
+            const int32_t t = static_cast<int32_t>(2 * bb);
+            a.t_a[t] = static_cast<int32_t>(uc); a.t_b[t] = static_cast<int32_t>(ic); a.t_g[t] = gp;
+            a.t_a[t + 1] = static_cast<int32_t>(nu); a.t_b[t + 1] = static_cast<int32_t>(nj); a.t_g[t + 1] = gn;
+            if (gp != 0.f) { atomicAdd(a.seg.cnt + uc, 1); atomicAdd(a.seg.cnt + a.U + ic, 1); }
+            if (gn != 0.f) { atomicAdd(a.seg.cnt + nu, 1); atomicAdd(a.seg.cnt + a.U + nj, 1); }
+        }
+    }
+
+    // deterministic loss reduction: fixed tree per block, fixed order over blocks
+    const float bsum = block_sum<MF_THREADS>(lsum, sh_red);
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        a.partial[blockIdx.x] = bsum;
+        __threadfence();
+        is_last = atomicAdd(a.done, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        float v = 0.f;
+        for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += 32)
+            v += *reinterpret_cast<volatile float*>(a.partial + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) { *a.loss_out = v * invB; *a.done = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(256) mf_fill_kernel(MfDev a) {
+    seg_rearm(a.seg);
+    const int64_t T = a.T;
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < T; t += nth) {
+        if (a.t_g[t] != 0.f) {
+            seg_place(a.seg, a.t_a[t], static_cast<int32_t>(t));
+            seg_place(a.seg, a.U + a.t_b[t], static_cast<int32_t>(t));
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(MF_THREADS) mf_bwd_kernel(MfDev a) {
+    constexpr int GROUPS = MF_THREADS / LPR;
+    constexpr int CAP = seg_sort_cap(LPR);
+    __shared__ int32_t sh_sort[GROUPS * 2 * CAP];
+    const int gl = threadIdx.x & (LPR - 1);
+    const int gib = threadIdx.x / LPR;
+    const unsigned gmask = group_mask(LPR);
+    int32_t* sh = sh_sort + gib * 2 * CAP;
+    const int D = a.D;
+    const int nseg = a.seg.totals[0];
+    const int nsegA = a.seg.totals[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
+        a.compact_counts[0] = nsegA;
+        a.compact_counts[1] = nseg - nsegA;
+    }
+    const int32_t* __restrict__ t_a = a.t_a;
+    const int32_t* __restrict__ t_b = a.t_b;
+    const float* __restrict__ t_g = a.t_g;
+
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * GROUPS + gib; s < nseg;
+         s += static_cast<int64_t>(gridDim.x) * GROUPS) {
+        const int start = a.seg.seg_start[s];
+        const int len = a.seg.seg_start[s + 1] - start;
+        const int64_t row = a.seg.seg_row[s];
+        const bool isA = s < nsegA;
+        const float* partner_tab = isA ? a.Wi : a.Wu;
+        const int32_t* partner_idx = isA ? t_b : t_a;
+        float bacc = 0.f;
+
+        float* out;
+        if (a.grad_mode == SLB_GRAD_DENSE) out = isA ? a.dWu + row * D : a.dWi + (row - a.U) * D;
+        else out = isA ? a.gWu + s * D : a.gWi + (s - nsegA) * D;
+
+        for (int c0 = 0; c0 < D; c0 += LPR * 4) {
+            const int c = c0 + gl * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float b2 = 0.f;
+            seg_visit_sorted<LPR>(a.seg.members, start, len, gl, gmask, sh, [&](int32_t t) {
+                const float g = t_g[t];
+                const float* prow = partner_tab + static_cast<int64_t>(partner_idx[t]) * D;
+                if (c < D) fma4(acc, g, ldg4(prow + c));
+                b2 += g;
+            });
+            if (c < D) st4(out + c, acc);
+            bacc = b2;
+        }
+        if (gl == 0) {
+            if (a.grad_mode == SLB_GRAD_DENSE) {
+                if (isA) a.dbu[row] = bacc; else a.dbi[row - a.U] = bacc;
+            } else {
+                if (isA) { a.urows[s] = row; a.gbu[s] = bacc; }
+                else { a.irows[s - nsegA] = row - a.U; a.gbi[s - nsegA] = bacc; }
+            }
+        }
+    }
+}
+
+// Fused row-wise optimizer over the compact gradient rows (touched rows only).
+// SGD:     W -= lr * (g + wd*W)
+// Adagrad: g' = g + wd*W; state += g'^2; W -= lr * g' / (sqrt(state) + eps)
+//          (torch.optim.Adagrad with lr_decay = 0, initial_accumulator_value = 0)
+template <int LPR>
+__global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
+    constexpr int GROUPS = MF_THREADS / LPR;
+    const int gl = threadIdx.x & (LPR - 1);
+    const int gib = threadIdx.x / LPR;
+    const int D = a.D;
+    const int nseg = a.seg.totals[0];
+    const int nsegA = a.seg.totals[2];
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * GROUPS + gib; s < nseg;
+         s += static_cast<int64_t>(gridDim.x) * GROUPS) {
+        const bool isA = s < nsegA;
+        const int64_t k = isA ? s : s - nsegA;
+        const int64_t row = isA ? a.urows[k] : a.irows[k];
+        float* W = (isA ? a.Wu : a.Wi) + row * D;
+        const float* G = (isA ? a.gWu : a.gWi) + k * D;
+        float* S = a.opt == SLB_OPT_ADAGRAD ? (isA ? a.sWu : a.sWi) + row * D : nullptr;
+        for (int c = gl * 4; c < D; c += LPR * 4) {
+            float4 w = ld4(W + c);
+            const float4 g0 = ld4(G + c);
+            float gv[4] = {g0.x + a.wd * w.x, g0.y + a.wd * w.y, g0.z + a.wd * w.z, g0.w + a.wd * w.w};
+            float wv[4] = {w.x, w.y, w.z, w.w};
+            if (a.opt == SLB_OPT_SGD) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wv[q] -= a.lr * gv[q];
+            } else {
+                float4 st = ld4(S + c);
+                float sv[4] = {st.x, st.y, st.z, st.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    sv[q] += gv[q] * gv[q];
+                    wv[q] -= a.lr * gv[q] / (sqrtf(sv[q]) + a.eps);
+                }
+                st4(S + c, make_float4(sv[0], sv[1], sv[2], sv[3]));
+            }
+            st4(W + c, make_float4(wv[0], wv[1], wv[2], wv[3]));
+        }
+        if (gl == 0) {
+            float* bw = (isA ? a.bu : a.bi) + row;
+            float g = (isA ? a.gbu : a.gbi)[k] + a.wd * *bw;
+            if (a.opt == SLB_OPT_SGD) {
+                *bw -= a.lr * g;
+            } else {
+                float* bs = (isA ? a.sbu : a.sbi) + row;
+                const float sv = *bs + g * g;
+                *bs = sv;
+                *bw -= a.lr * g / (sqrtf(sv) + a.eps);
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(MF_THREADS)
+mf_scores_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi,
+                 const float* __restrict__ bu, const float* __restrict__ bi, int D,
+                 const int64_t* __restrict__ users, const int64_t* __restrict__ items, int64_t n,
+                 int user_broadcast, float* __restrict__ scores) {
+    const int gl = threadIdx.x & (LPR - 1);
+    const unsigned gmask = group_mask(LPR);
+    constexpr int GROUPS = MF_THREADS / LPR;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / LPR;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * GROUPS;
+    const int64_t iters = (n + gstride - 1) / gstride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t b = gid + it * gstride;
+        const bool valid = b < n;
+        const int64_t bb = valid ? b : 0;
+        const int64_t u = users[user_broadcast ? 0 : bb], i = items[bb];
+        const float p = row_dot<LPR>(Wu + u * D, Wi + i * D, D, gl, gmask) + __ldg(bu + u) + __ldg(bi + i);
+        if (valid && gl == 0) scores[bb] = p;
+    }
+}
+
+// Terms from externally supplied score gradients (autograd of BilinearNet.forward).
+__global__ void __launch_bounds__(256)
+mf_terms_kernel(MfDev a, const float* __restrict__ gscores, int user_broadcast) {
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < a.T; t += nth) {
+        int64_t u = a.users[user_broadcast ? 0 : t], i = a.items[t];
+        float g = gscores[t];
+        if (u < 0 || u >= a.U || i < 0 || i >= a.I) { atomicExch(a.err, 1); u = 0; i = 0; g = 0.f; }
+        a.t_a[t] = static_cast<int32_t>(u); a.t_b[t] = static_cast<int32_t>(i); a.t_g[t] = g;
+        if (g != 0.f) { atomicAdd(a.seg.cnt + u, 1); atomicAdd(a.seg.cnt + a.U + i, 1); }
+    }
+}
+
+struct MfLayout {
+    int32_t* t_a; int32_t* t_b; float* t_g; float* partial; int32_t* done; int32_t* err;
+    SegIndex seg;
+    size_t bytes;
+};
+
+constexpr int MF_MAX_GRID = 148 * 16;
+
+MfLayout mf_layout(void* base, int64_t B, int64_t U, int64_t I) {
+    WsCarver ws(base);
+    MfLayout l;
+    // persistent (zero-at-rest) part first
+    l.done = ws.take<int32_t>(8);
+    l.err = l.done + 4;
+    l.seg = seg_index_carve(ws, U + I, 4 * B);
+    l.t_a = ws.take<int32_t>(2 * B);
+    l.t_b = ws.take<int32_t>(2 * B);
+    l.t_g = ws.take<float>(2 * B);
+    l.partial = ws.take<float>(MF_MAX_GRID);
+    l.bytes = ws.bytes();
+    return l;
+}
+
+int lpr_for_dim(int D) {
+    int l = D / 4;
+    if (l >= 32) return 32;
+    int p = 1;
+    while (p < l) p <<= 1;
+    return p;
+}
+
+#define DISPATCH_LPR(lpr, KERNEL, grid, block, stream, ...)                                   \
+    switch (lpr) {                                                                           \
+        case 1: KERNEL<1><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                   \
+        case 2: KERNEL<2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                   \
+        case 4: KERNEL<4><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                   \
+        case 8: KERNEL<8><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                   \
+        case 16: KERNEL<16><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                 \
+        default: KERNEL<32><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                 \
+    }
+
+int validate(const slb_mf_step_args* x) {
+    SLB_REQUIRE(x != nullptr, "mf_train_step: null args");
+    SLB_REQUIRE(x->batch > 0, "mf_train_step: batch must be > 0");
+    SLB_REQUIRE(x->dim >= 4 && x->dim % 4 == 0, "mf_train_step: dim must be a positive multiple of 4 (got %d)", x->dim);
+    SLB_REQUIRE(x->loss >= 0 && x->loss <= 3, "mf_train_step: bad loss kind %d", x->loss);
+    SLB_REQUIRE(x->n_neg >= 1, "mf_train_step: n_neg must be >= 1");
+    SLB_REQUIRE(x->loss == SLB_LOSS_ADAPTIVE_HINGE || x->n_neg == 1, "mf_train_step: n_neg > 1 only for adaptive hinge");
+    SLB_REQUIRE(x->num_users > 0 && x->num_items > 0, "mf_train_step: empty tables");
+    SLB_REQUIRE(x->num_users + x->num_items < (1ll << 31) - SEG_SCAN_TILE, "mf_train_step: num_users + num_items must be < 2^31");
+    SLB_REQUIRE(x->batch * 4 < (1ll << 31), "mf_train_step: batch too large");
+    SLB_REQUIRE(x->users && x->items && x->negs && x->Wu && x->Wi && x->bu && x->bi && x->loss_out,
+                "mf_train_step: null pointer");
+    SLB_REQUIRE(x->workspace != nullptr, "mf_train_step: null workspace");
+    if (x->grad_mode == SLB_GRAD_DENSE) {
+        SLB_REQUIRE(x->dWu && x->dWi && x->dbu && x->dbi, "mf_train_step: dense mode needs dWu/dWi/dbu/dbi");
+        SLB_REQUIRE(x->opt == SLB_OPT_NONE, "mf_train_step: fused optimizer needs compact grads");
+    } else {
+        SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT, "mf_train_step: bad grad_mode");
+        SLB_REQUIRE(x->urows && x->gWu && x->gbu && x->irows && x->gWi && x->gbi && x->compact_counts,
+                    "mf_train_step: compact mode needs urows/gWu/gbu/irows/gWi/gbi/compact_counts");
+    }
+    SLB_REQUIRE(x->opt >= SLB_OPT_NONE && x->opt <= SLB_OPT_ADAGRAD, "mf_train_step: bad optimizer");
+    if (x->opt == SLB_OPT_ADAGRAD)
+        SLB_REQUIRE(x->state_Wu && x->state_Wi && x->state_bu && x->state_bi, "mf_train_step: adagrad needs state");
+    const size_t need = slb_mf_step_workspace_bytes(x->batch, x->n_neg, x->loss, x->num_users, x->num_items);
+    if (x->workspace_bytes < need) {
+        slb_set_error("mf_train_step: workspace too small (%zu < %zu)", x->workspace_bytes, need);
+        return SLB_ENOSPC;
+    }
+    return SLB_OK;
+}
+
+int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
+                const int64_t* negs, int64_t B, float* loss_out, cudaStream_t st) {
+    // layout is sized for x->batch so that short last batches reuse the same carve
+    MfLayout l = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
+    MfDev a;
+    a.B = B; a.T = 2 * B; a.users = users; a.items = items; a.negs = negs;
+    a.loss = x->loss; a.n_neg = x->n_neg;
+    a.U = x->num_users; a.I = x->num_items; a.D = x->dim;
+    a.Wu = x->Wu; a.Wi = x->Wi; a.bu = x->bu; a.bi = x->bi;
+    a.loss_out = loss_out; a.pos_out = x->pos_out; a.neg_out = x->neg_out;
+    a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
+    a.seg = l.seg;
+    a.grad_mode = x->grad_mode;
+    a.dWu = x->dWu; a.dWi = x->dWi; a.dbu = x->dbu; a.dbi = x->dbi;
+    a.urows = x->urows; a.gWu = x->gWu; a.gbu = x->gbu;
+    a.irows = x->irows; a.gWi = x->gWi; a.gbi = x->gbi;
+    a.compact_counts = x->compact_counts;
+    a.opt = x->opt; a.lr = x->lr; a.wd = x->weight_decay; a.eps = x->eps;
+    a.sWu = x->state_Wu; a.sWi = x->state_Wi; a.sbu = x->state_bu; a.sbi = x->state_bi;
+
+    const int lpr = lpr_for_dim(x->dim);
+    const int groups = MF_THREADS / lpr;
+    const int sms = slb_sms();
+    int64_t want = (B + groups - 1) / groups;
+    int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 8 ? want : static_cast<int64_t>(sms) * 8);
+    if (grid < 1) grid = 1;
+    if (grid > MF_MAX_GRID) grid = MF_MAX_GRID;
+    DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
+    SLB_LAUNCH_CHECK("mf_fwd_kernel");
+    seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
+    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    int fgrid = static_cast<int>((2 * B + 255) / 256);
+    if (fgrid > sms * 8) fgrid = sms * 8;
+    mf_fill_kernel<<<fgrid, 256, 0, st>>>(a);
+    SLB_LAUNCH_CHECK("mf_fill_kernel");
+    int64_t bwant = (2 * B + groups - 1) / groups;
+    int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
+    DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_kernel");
+    if (x->opt != SLB_OPT_NONE) {
+        DISPATCH_LPR(lpr, mf_apply_kernel, bgrid, MF_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_apply_kernel");
+    }
+    return SLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t slb_mf_step_workspace_bytes(int64_t batch, int32_t n_neg, int32_t loss,
+                                   int64_t num_users, int64_t num_items) {
+    (void)n_neg; (void)loss;
+    return mf_layout(nullptr, batch, num_users, num_items).bytes;
+}
+
+int64_t slb_mf_compact_rows(int64_t batch, int32_t n_neg, int32_t loss, int32_t which) {
+    (void)n_neg; (void)loss; (void)which;
+    return 2 * batch;  // positive + selected negative term per interaction
+}
+
+int slb_mf_train_step(const slb_mf_step_args* x, slb_stream_t stream) {
+    const int rc = validate(x);
+    if (rc != SLB_OK) return rc;
+    return launch_step(x, x->users, x->items, x->negs, x->batch, x->loss_out,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int slb_mf_fit_epoch(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
+                     const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream) {
+    slb_mf_step_args tmp = *x;
+    tmp.users = users; tmp.items = items; tmp.negs = negs; tmp.loss_out = losses_out;
+    const int rc = validate(&tmp);
+    if (rc != SLB_OK) return rc;
+    SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT && x->opt != SLB_OPT_NONE,
+                "mf_fit_epoch: needs compact grads and a fused optimizer");
+    SLB_REQUIRE(n > 0, "mf_fit_epoch: n must be > 0");
+    int64_t step = 0;
+    for (int64_t lo = 0; lo < n; lo += x->batch, ++step) {
+        const int64_t B = n - lo < x->batch ? n - lo : x->batch;
+        // adaptive hinge: negatives of step k are the flat [B*n_neg] block the
+        // reference's per-batch randint would have produced (implicit.py:256-259)
+        const int64_t* ng = negs + lo * x->n_neg;
+        const int r = launch_step(x, users + lo, items + lo, ng, B, losses_out + step,
+                                  static_cast<cudaStream_t>(stream));
+        if (r != SLB_OK) return r;
+    }
+    return SLB_OK;
+}
+
+int slb_mf_scores(const float* Wu, const float* Wi, const float* bu, const float* bi,
+                  int32_t dim, const int64_t* users, const int64_t* items, int64_t n,
+                  int32_t user_broadcast, float* scores, slb_stream_t stream) {
+    SLB_REQUIRE(dim >= 4 && dim % 4 == 0, "mf_scores: dim must be a positive multiple of 4 (got %d)", dim);
+    SLB_REQUIRE(Wu && Wi && bu && bi && users && items && scores, "mf_scores: null pointer");
+    if (n <= 0) return SLB_OK;
+    const int lpr = lpr_for_dim(dim);
+    const int groups = MF_THREADS / lpr;
+    const int sms = slb_sms();
+    int64_t want = (n + groups - 1) / groups;
+    int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 8 ? want : static_cast<int64_t>(sms) * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_LPR(lpr, mf_scores_kernel, grid, MF_THREADS, st, Wu, Wi, bu, bi, dim, users, items, n,
+                 user_broadcast, scores);
+    SLB_LAUNCH_CHECK("mf_scores_kernel");
+    return SLB_OK;
+}
+
+int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int64_t* items,
+                           int64_t n, int32_t user_broadcast, const float* Wu, const float* Wi,
+                           int64_t num_users, int64_t num_items, int32_t dim,
+                           float* dWu, float* dWi, float* dbu, float* dbi,
+                           void* workspace, size_t workspace_bytes, slb_stream_t stream) {
+    SLB_REQUIRE(dim >= 4 && dim % 4 == 0, "mf_scores_backward: dim must be a positive multiple of 4 (got %d)", dim);
+    SLB_REQUIRE(gscores && users && items && Wu && Wi && dWu && dWi && dbu && dbi && workspace,
+                "mf_scores_backward: null pointer");
+    SLB_REQUIRE(num_users + num_items < (1ll << 31) - SEG_SCAN_TILE && n * 2 < (1ll << 31), "mf_scores_backward: too large");
+    if (n <= 0) return SLB_OK;
+    const int64_t Bcap = (n + 1) / 2;           // layout holds 2*Bcap >= n terms
+    MfLayout l = mf_layout(workspace, Bcap, num_users, num_items);
+    if (workspace_bytes < l.bytes) {
+        slb_set_error("mf_scores_backward: workspace too small (%zu < %zu)", workspace_bytes, l.bytes);
+        return SLB_ENOSPC;
+    }
+    MfDev a = {};
+    a.B = n; a.T = n; a.users = users; a.items = items;
+    a.U = num_users; a.I = num_items; a.D = dim;
+    a.Wu = const_cast<float*>(Wu); a.Wi = const_cast<float*>(Wi);
+    a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
+    a.seg = l.seg;
+    a.grad_mode = SLB_GRAD_DENSE;
+    a.dWu = dWu; a.dWi = dWi; a.dbu = dbu; a.dbi = dbi;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int sms = slb_sms();
+    int g1 = static_cast<int>((n + 255) / 256);
+    if (g1 > sms * 8) g1 = sms * 8;
+    mf_terms_kernel<<<g1, 256, 0, st>>>(a, gscores, user_broadcast);
+    SLB_LAUNCH_CHECK("mf_terms_kernel");
+    seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
+    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    mf_fill_kernel<<<g1, 256, 0, st>>>(a);
+    SLB_LAUNCH_CHECK("mf_fill_kernel");
+    const int lpr = lpr_for_dim(dim);
+    const int groups = MF_THREADS / lpr;
+    int64_t bwant = (n + groups - 1) / groups;
+    int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
+    DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_kernel");
+    return SLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// Device-side NumPy-legacy RandomState stream: MT19937 block generation and the
+// masked-rejection bounded draw that spotlight/sampling.py:34
+// (random_state.randint(0, num_items, shape, dtype=int64)) consumes.
+//
+// The stream is stored as consecutive 624-word *untempered* key blocks so the
+// host can hand the state back to numpy (RandomState.set_state) at any word.
+//
+// mt19937_fill_kernel: the MT recurrence has dependency distance 227
+// (x[k+624] needs x[k], x[k+1], x[k+397]); one CTA advances a block in three
+// barrier-separated rounds (227 + 227 + 170 words) out of shared memory and
+// streams the blocks to HBM.  It is latency-bound on one SM by construction
+// (~10 G words/s); it runs on a side stream ahead of the consumer.
+//
+// sample_* kernels: parallel stream compaction of the accepted words
+// (tile counts -> scan -> ordered scatter), bit-exact with numpy's sequential
+// loop because acceptance of a word does not depend on earlier words.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MT_N = 624;
+constexpr int MT_M = 397;
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+__global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* blocks, int64_t nblocks) {
+    __shared__ uint32_t buf[2][MT_N + 1];
+    const int t = threadIdx.x;
+    for (int k = t; k < MT_N; k += 256) buf[0][k] = blocks[k];
+    __syncthreads();
+    int cur = 0;
+    for (int64_t blk = 1; blk < nblocks; ++blk) {
+        const uint32_t* o = buf[cur];
+        uint32_t* n = buf[cur ^ 1];
+        if (t < 227) n[t] = mt_mix(o[t], o[t + 1], o[t + MT_M]);
+        __syncthreads();
+        if (t < 227) n[227 + t] = mt_mix(o[227 + t], o[228 + t], n[t]);
+        __syncthreads();
+        if (t < 169) n[454 + t] = mt_mix(o[454 + t], o[455 + t], n[227 + t]);
+        if (t == 169) n[623] = mt_mix(o[623], n[0], n[396]);
+        __syncthreads();
+        uint32_t* dst = blocks + blk * MT_N;
+        for (int k = t; k < MT_N; k += 256) dst[k] = n[k];
+        // no 4th barrier: the next round only writes the *old* buffer, whose last
+        // readers ran before the 3rd barrier; the stores above read the new one
+        cur ^= 1;
+    }
+}
+
+constexpr int SMP_THREADS = 256;
+constexpr int SMP_ITEMS = 8;
+constexpr int SMP_TILE = SMP_THREADS * SMP_ITEMS;
+
+__global__ void __launch_bounds__(SMP_THREADS)
+sample_count_kernel(const uint32_t* __restrict__ blocks, int64_t nwords, const int64_t* cursor,
+                    uint32_t rng, uint32_t mask, uint32_t* tile_cnt) {
+    __shared__ uint32_t sh[SMP_THREADS / 32];
+    const int64_t start = cursor[0];
+    const int64_t base = start + static_cast<int64_t>(blockIdx.x) * SMP_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < SMP_ITEMS; ++i) {
+        const int64_t w = base + i * SMP_THREADS + threadIdx.x;
+        if (w < nwords) c += (mt_temper(blocks[w]) & mask) <= rng;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < SMP_THREADS / 32; ++k) s += sh[k];
+        tile_cnt[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of tile counts by one block (ntiles is at most a few 10^4)
+__global__ void __launch_bounds__(1024)
+sample_scan_kernel(const uint32_t* tile_cnt, int64_t ntiles, int64_t* tile_off) {
+    __shared__ int64_t sh[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (ntiles + 1023) / 1024;
+    const int64_t lo = t * per, hi = lo + per < ntiles ? lo + per : ntiles;
+    int64_t s = 0;
+    for (int64_t k = lo; k < hi; ++k) s += tile_cnt[k];
+    sh[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int64_t v = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    int64_t run = sh[t] - s;
+    for (int64_t k = lo; k < hi; ++k) { tile_off[k] = run; run += tile_cnt[k]; }
+    if (t == 1023) tile_off[ntiles] = sh[1023];
+}
+
+__global__ void __launch_bounds__(SMP_THREADS)
+sample_scatter_kernel(const uint32_t* __restrict__ blocks, int64_t nwords, int64_t* cursor,
+                      uint32_t rng, uint32_t mask, int64_t count, const int64_t* tile_off,
+                      int64_t ntiles, int64_t* out, int64_t* result) {
+    __shared__ uint32_t sh[SMP_THREADS / 32];
+    const int64_t start = cursor[0];
+    // blocked arrangement so that ranks follow stream order
+    const int64_t base = start + static_cast<int64_t>(blockIdx.x) * SMP_TILE + threadIdx.x * SMP_ITEMS;
+    uint32_t v[SMP_ITEMS];
+    bool ok[SMP_ITEMS];
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < SMP_ITEMS; ++i) {
+        const int64_t w = base + i;
+        v[i] = w < nwords ? mt_temper(blocks[w]) & mask : 0xffffffffu;
+        ok[i] = w < nwords && v[i] <= rng;
+        c += ok[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    uint32_t wpre = 0;
+    for (int k = 0; k < warp; ++k) wpre += sh[k];
+    int64_t rank = tile_off[blockIdx.x] + wpre + inc - c;
+#pragma unroll
+    for (int i = 0; i < SMP_ITEMS; ++i) {
+        if (ok[i]) {
+            if (rank < count) out[rank] = static_cast<int64_t>(v[i]);
+            if (rank == count - 1) result[0] = base + i + 1;   // one past last consumed word
+            ++rank;
+        }
+    }
+    if (blockIdx.x == ntiles - 1 && threadIdx.x == SMP_THREADS - 1) {
+        const int64_t total = tile_off[ntiles];
+        result[1] = total < count ? total : count;
+        if (total < count) result[0] = nwords;                  // stream exhausted
+    }
+}
+
+__global__ void sample_commit_kernel(int64_t* cursor, const int64_t* result) {
+    cursor[0] = result[0];
+    cursor[1] = result[1];
+}
+
+}  // namespace
+
+extern "C" {
+
+int slb_mt19937_fill(uint32_t* blocks, int64_t nblocks, slb_stream_t stream) {
+    SLB_REQUIRE(blocks != nullptr && nblocks >= 1, "mt19937_fill: bad arguments");
+    if (nblocks == 1) return SLB_OK;
+    mt19937_fill_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(blocks, nblocks);
+    SLB_LAUNCH_CHECK("mt19937_fill_kernel");
+    return SLB_OK;
+}
+
+size_t slb_sample_workspace_bytes(int64_t nwords) {
+    const int64_t ntiles = (nwords + SMP_TILE - 1) / SMP_TILE + 1;
+    WsCarver ws(nullptr);
+    ws.take<uint32_t>(ntiles);
+    ws.take<int64_t>(ntiles + 1);
+    ws.take<int64_t>(2);
+    return ws.bytes();
+}
+
+int slb_sample_bounded(const uint32_t* blocks, int64_t nwords, int64_t* cursor, uint32_t rng,
+                       int64_t count, int64_t* out, void* workspace, size_t workspace_bytes,
+                       slb_stream_t stream) {
+    SLB_REQUIRE(blocks && cursor && out && workspace, "sample_bounded: null pointer");
+    SLB_REQUIRE(count > 0 && nwords > 0, "sample_bounded: count and nwords must be > 0");
+    SLB_REQUIRE(rng != 0 && rng != 0xffffffffu, "sample_bounded: rng must be in [1, 2^32 - 2]");
+    if (workspace_bytes < slb_sample_workspace_bytes(nwords)) {
+        slb_set_error("sample_bounded: workspace too small");
+        return SLB_ENOSPC;
+    }
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    // tiles are laid out from the cursor; the host bounds them by nwords (cursor >= 0)
+    const int64_t ntiles = (nwords + SMP_TILE - 1) / SMP_TILE;
+    WsCarver ws(workspace);
+    uint32_t* tile_cnt = ws.take<uint32_t>(ntiles + 1);
+    int64_t* tile_off = ws.take<int64_t>(ntiles + 1);
+    int64_t* result = ws.take<int64_t>(2);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    sample_count_kernel<<<static_cast<unsigned>(ntiles), SMP_THREADS, 0, st>>>(blocks, nwords, cursor, rng, mask, tile_cnt);
+    SLB_LAUNCH_CHECK("sample_count_kernel");
+    sample_scan_kernel<<<1, 1024, 0, st>>>(tile_cnt, ntiles, tile_off);
+    SLB_LAUNCH_CHECK("sample_scan_kernel");
+    sample_scatter_kernel<<<static_cast<unsigned>(ntiles), SMP_THREADS, 0, st>>>(blocks, nwords, cursor, rng, mask, count,
+                                                                 tile_off, ntiles, out, result);
+    SLB_LAUNCH_CHECK("sample_scatter_kernel");
+    sample_commit_kernel<<<1, 1, 0, st>>>(cursor, result);
+    SLB_LAUNCH_CHECK("sample_commit_kernel");
+    return SLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// Segment index: the per-batch inverted index that makes the gradient scatter
+// deterministic.  Given T "terms" each keyed by a row id in [0, R), build
+//   seg_row[s], seg_start[s]  (s = 0..nseg-1, rows ascending), members[]
+// so that members[seg_start[s] .. seg_start[s+1]) are the term ids whose key is
+// seg_row[s].  One group of lanes then owns each touched row, sums its
+// contributions in ascending term order and writes the row once: no float
+// atomics, bit-reproducible, replaces aten::embedding_dense_backward's
+// index_add (reference: autograd of spotlight/layers.py:23-56 lookups).
+//
+// Pipeline (all asynchronous on one stream):
+//   count   integer atomicAdd into cnt[R]            (fused into the producer)
+//   scan    single-pass decoupled look-back scan of cnt -> off, segment list
+//   fill    members[off[row] + atomicSub(cnt[row])-1] = term  (restores cnt=0)
+//   reduce  consumer kernel; sorts each (tiny) member list, then accumulates
+//
+// HBM/L2 bytes: cnt read 4R (L2-resident for item tables), everything else
+// O(T).  cnt/status/ticket are all-zero at rest.
+#pragma once
+
+#include "common.cuh"
+
+constexpr int SEG_SCAN_THREADS = 256;
+constexpr int SEG_SCAN_ITEMS = 16;
+constexpr int SEG_SCAN_TILE = SEG_SCAN_THREADS * SEG_SCAN_ITEMS;  // 4096
+
+struct SegIndex {
+    int32_t* cnt;        // [Rpad] zero at rest
+    int32_t* off;        // [Rpad] exclusive prefix of cnt (valid where cnt > 0)
+    unsigned long long* status;  // [ntiles] look-back words, zero at rest
+    int32_t* ticket;     // [1] dynamic tile id, zero at rest
+    int32_t* totals;     // [4] nseg, nterms, nsegA, (unused)
+    int32_t* seg_row;    // [Tmax]
+    int32_t* seg_start;  // [Tmax + 1]
+    int32_t* members;    // [Tmax]
+    int64_t R;           // key space size
+    int64_t Rpad;
+    int64_t ntiles;
+    int64_t Tmax;
+};
+
+// Lays the index out in a caller workspace.  Pass base == nullptr to size it.
+static inline SegIndex seg_index_carve(WsCarver& ws, int64_t R, int64_t Tmax) {
+    SegIndex s;
+    s.R = R;
+    s.Rpad = (R + SEG_SCAN_TILE - 1) / SEG_SCAN_TILE * SEG_SCAN_TILE;
+    s.ntiles = s.Rpad / SEG_SCAN_TILE;
+    s.Tmax = Tmax;
+    s.cnt = ws.take<int32_t>(s.Rpad);
+    s.off = ws.take<int32_t>(s.Rpad);
+    s.status = ws.take<unsigned long long>(s.ntiles);
+    s.ticket = ws.take<int32_t>(8);
+    s.totals = s.ticket + 4;
+    s.seg_row = ws.take<int32_t>(Tmax + 1);
+    s.seg_start = ws.take<int32_t>(Tmax + 2);
+    s.members = ws.take<int32_t>(Tmax + 1);
+    return s;
+}
+
+#ifdef __CUDACC__
+
+// status word: [63:62] flag, [61:31] nonzero-count, [30:0] sum
+#define SEG_FLAG_AGG 1ull
+#define SEG_FLAG_INC 2ull
+__device__ __forceinline__ unsigned long long seg_pack(unsigned long long flag, uint32_t sum, uint32_t nz) {
+    return (flag << 62) | (static_cast<unsigned long long>(nz) << 31) | sum;
+}
+__device__ __forceinline__ uint32_t seg_sum(unsigned long long v) { return static_cast<uint32_t>(v & 0x7fffffffull); }
+__device__ __forceinline__ uint32_t seg_nz(unsigned long long v) { return static_cast<uint32_t>((v >> 31) & 0x7fffffffull); }
+__device__ __forceinline__ unsigned long long seg_flag(unsigned long long v) { return v >> 62; }
+
+// Single-pass scan of cnt[0..Rpad): off = exclusive prefix sum; every non-zero
+// row gets a compact segment id (exclusive prefix of [cnt > 0]).
+// RA: rows < RA belong to key space A; totals[2] = number of A segments.
+static __global__ void __launch_bounds__(SEG_SCAN_THREADS)
+seg_scan_kernel(SegIndex s, int64_t RA) {
+    __shared__ int32_t sh_tile;
+    __shared__ uint32_t sh_wsum[SEG_SCAN_THREADS / 32], sh_wnz[SEG_SCAN_THREADS / 32];
+    __shared__ uint32_t sh_prefix_sum, sh_prefix_nz;
+
+    if (threadIdx.x == 0) sh_tile = atomicAdd(s.ticket, 1);
+    __syncthreads();
+    const int tile = sh_tile;
+    const int64_t base = static_cast<int64_t>(tile) * SEG_SCAN_TILE + threadIdx.x * SEG_SCAN_ITEMS;
+
+    int32_t c[SEG_SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SEG_SCAN_ITEMS / 4; ++i) {
+        const int4 v = *reinterpret_cast<const int4*>(s.cnt + base + 4 * i);
+        c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+    }
+    uint32_t tsum = 0, tnz = 0;
+#pragma unroll
+    for (int i = 0; i < SEG_SCAN_ITEMS; ++i) { tsum += c[i]; tnz += c[i] != 0; }
+
+    // warp inclusive scans
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t isum = tsum, inz = tnz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, isum, o);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, inz, o);
+        if (lane >= o) { isum += a; inz += b; }
+    }
+    if (lane == 31) { sh_wsum[warp] = isum; sh_wnz[warp] = inz; }
+    __syncthreads();
+    uint32_t wsum = 0, wnz = 0, bsum = 0, bnz = 0;
+#pragma unroll
+    for (int w = 0; w < SEG_SCAN_THREADS / 32; ++w) {
+        if (w < warp) { wsum += sh_wsum[w]; wnz += sh_wnz[w]; }
+        bsum += sh_wsum[w]; bnz += sh_wnz[w];
+    }
+    const uint32_t esum = wsum + isum - tsum;   // exclusive within the tile
+    const uint32_t enz = wnz + inz - tnz;
+
+    // decoupled look-back by warp 0
+    if (warp == 0) {
+        volatile unsigned long long* st = s.status;
+        uint32_t psum = 0, pnz = 0;
+        if (tile == 0) {
+            if (lane == 0) st[0] = seg_pack(SEG_FLAG_INC, bsum, bnz);
+        } else {
+            if (lane == 0) st[tile] = seg_pack(SEG_FLAG_AGG, bsum, bnz);
+            int j = tile - 1 - lane;
+            while (true) {
+                unsigned long long v = 0;
+                if (j >= 0) {
+                    do { v = st[j]; } while (seg_flag(v) == 0);
+                } else {
+                    v = seg_pack(SEG_FLAG_INC, 0, 0);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, seg_flag(v) == SEG_FLAG_INC);
+                // lanes at or before the first INCLUSIVE predecessor contribute
+                const int first = inc ? __ffs(inc) - 1 : 32;
+                uint32_t cs = lane <= first ? seg_sum(v) : 0u;
+                uint32_t cz = lane <= first ? seg_nz(v) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                    cz += __shfl_xor_sync(0xffffffffu, cz, o);
+                }
+                psum += cs; pnz += cz;
+                if (inc) break;
+                j -= 32;
+            }
+            if (lane == 0) st[tile] = seg_pack(SEG_FLAG_INC, psum + bsum, pnz + bnz);
+        }
+        if (lane == 0) { sh_prefix_sum = psum; sh_prefix_nz = pnz; }
+    }
+    __syncthreads();
+    uint32_t run = sh_prefix_sum + esum;
+    uint32_t seg = sh_prefix_nz + enz;
+
+#pragma unroll
+    for (int i = 0; i < SEG_SCAN_ITEMS; ++i) {
+        const int64_t row = base + i;
+        if (row == RA) s.totals[2] = static_cast<int32_t>(seg);
+        if (c[i] != 0) {
+            s.off[row] = static_cast<int32_t>(run);
+            s.seg_row[seg] = static_cast<int32_t>(row);
+            s.seg_start[seg] = static_cast<int32_t>(run);
+            run += c[i];
+            ++seg;
+        }
+    }
+    if (tile == s.ntiles - 1 && threadIdx.x == SEG_SCAN_THREADS - 1) {
+        s.totals[0] = static_cast<int32_t>(seg);
+        s.totals[1] = static_cast<int32_t>(run);
+        s.seg_start[seg] = static_cast<int32_t>(run);
+        if (RA >= s.Rpad) s.totals[2] = static_cast<int32_t>(seg);
+    }
+}
+
+// Re-arms the scan for the next use; run by any later kernel of the chain.
+__device__ __forceinline__ void seg_rearm(const SegIndex& s) {
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = tid; i < s.ntiles; i += nth) s.status[i] = 0ull;
+    if (tid == 0) *s.ticket = 0;
+}
+
+// members[off[key] + (--cnt[key])] = term.  Afterwards cnt is all-zero again.
+__device__ __forceinline__ void seg_place(const SegIndex& s, int64_t key, int32_t term) {
+    const int32_t old = atomicSub(s.cnt + key, 1);
+    s.members[s.off[key] + old - 1] = term;
+}
+
+// Hands `visit(term)` the member terms of one segment in ascending term order.
+// G lanes of one group cooperate; all G lanes call with identical (start, len).
+// sh: 2 * seg_sort_cap(G) ints of shared scratch private to the group.
+__host__ __device__ constexpr int seg_sort_cap(int G) { return G >= 4 ? 64 : 16 * G; }
+
+template <int G, typename F>
+__device__ __forceinline__ void seg_visit_sorted(const int32_t* __restrict__ members, int start,
+                                                 int len, int gl /* lane in group */,
+                                                 unsigned gmask, int32_t* sh, F visit) {
+    if (len == 1) {
+        visit(members[start]);
+        return;
+    }
+    if (len == 2) {
+        const int32_t a = members[start], b = members[start + 1];
+        visit(a < b ? a : b);
+        visit(a < b ? b : a);
+        return;
+    }
+    constexpr int CAP = seg_sort_cap(G);
+    if (len <= CAP) {
+        // rank-by-counting through shared scratch (term ids are distinct)
+        int32_t* in = sh;
+        int32_t* out = sh + CAP;
+        for (int i = gl; i < len; i += G) in[i] = members[start + i];
+        __syncwarp(gmask);
+        for (int i = gl; i < len; i += G) {
+            const int32_t m = in[i];
+            int r = 0;
+            for (int j = 0; j < len; ++j) r += in[j] < m;
+            out[r] = m;
+        }
+        __syncwarp(gmask);
+        for (int i = 0; i < len; ++i) visit(out[i]);
+        __syncwarp(gmask);
+        return;
+    }
+    // long segment (hot row): repeated min-selection straight from global
+    // memory.  O(len^2 / G) but correct for any length.
+    int32_t last = -1;
+    for (int i = 0; i < len; ++i) {
+        int32_t best = 0x7fffffff;
+        for (int j = gl; j < len; j += G) {
+            const int32_t m = members[start + j];
+            if (m > last && m < best) best = m;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const int32_t other = __shfl_xor_sync(gmask, best, o);
+            best = other < best ? other : best;
+        }
+        visit(best);
+        last = best;
+    }
+}
+
+#endif  // __CUDACC__

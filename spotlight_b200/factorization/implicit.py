@@ -1,0 +1,280 @@
+"""Implicit-feedback factorization model with the reference's estimator API
+(spotlight/factorization/implicit.py:22-311): same constructor arguments,
+``fit(interactions, verbose)``, ``predict(user_ids, item_ids=None)``, private
+attributes (``_net``, ``_optimizer``, ``_random_state``, ``_num_users``,
+``_num_items``) and error behaviour.
+
+What changed is where the ``fit`` loop body runs.  Three routes, chosen per
+model, all producing the reference's losses and gradients:
+
+``epoch pipeline``   BilinearNet with plain tables + a fused optimizer
+                     (:mod:`spotlight_b200.optim`): the whole epoch -- negative
+                     draw, fused forward kernel, deterministic gradient kernel,
+                     row-wise optimizer -- is enqueued by one C call and the
+                     host reads the per-batch losses once at the end.
+``fused autograd``   BilinearNet with plain tables + any ``torch.optim``
+                     optimizer (incl. the reference's default dense Adam): one
+                     fused op per minibatch fills dense ``.grad``.
+``generic``          custom ``representation`` / Bloom layers: the reference's
+                     loop shape over this package's gather and loss ops.
+
+There is no CPU route: ``use_cuda=False`` raises at ``fit``.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from spotlight_b200 import _lib, ops
+from spotlight_b200.factorization._components import _predict_process_ids
+from spotlight_b200.factorization.representations import BilinearNet
+from spotlight_b200.helpers import _repr_model
+from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
+from spotlight_b200.sampling import sample_items
+from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffle
+
+_NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
+           'route; construct the model with use_cuda=True.')
+
+
+class ImplicitFactorizationModel(object):
+    """Implicit feedback matrix factorization trained by negative sampling.
+
+    Parameters (identical to the reference, implicit.py:76-88)
+    ----------
+    loss: 'pointwise' | 'bpr' | 'hinge' | 'adaptive_hinge'
+    embedding_dim, n_iter, batch_size, l2, learning_rate
+    optimizer_func: callable(params) -> torch optimizer; default is the
+        reference's dense ``Adam(weight_decay=l2, lr=learning_rate)``.  Pass
+        :func:`spotlight_b200.optim.fused_adagrad` / ``fused_sgd`` for the
+        on-device epoch pipeline.
+    use_cuda: must be True to ``fit`` / ``predict``.
+    representation: optional custom network module.
+    sparse: use sparse gradients for embedding layers.
+    random_state: ``numpy.random.RandomState`` driving shuffling and negative
+        sampling (one MT19937 stream, consumed exactly as the reference does).
+    num_negative_samples: negatives per positive for adaptive hinge.
+    """
+
+    def __init__(self, loss='pointwise', embedding_dim=32, n_iter=10, batch_size=256, l2=0.0,
+                 learning_rate=1e-2, optimizer_func=None, use_cuda=False, representation=None,
+                 sparse=False, random_state=None, num_negative_samples=5):
+
+        assert loss in ('pointwise', 'bpr', 'hinge', 'adaptive_hinge')
+
+        self._loss = loss
+        self._embedding_dim = embedding_dim
+        self._n_iter = n_iter
+        self._learning_rate = learning_rate
+        self._batch_size = batch_size
+        self._l2 = l2
+        self._use_cuda = use_cuda
+        self._representation = representation
+        self._sparse = sparse
+        self._optimizer_func = optimizer_func
+        self._random_state = random_state or np.random.RandomState()
+        self._num_negative_samples = num_negative_samples
+
+        self._num_users = None
+        self._num_items = None
+        self._net = None
+        self._optimizer = None
+        self._loss_func = None
+
+        # same stream position as the reference (implicit.py:114)
+        set_seed(self._random_state.randint(-10**8, 10**8), cuda=self._use_cuda)
+
+    def __repr__(self):
+        return _repr_model(self)
+
+    @property
+    def _initialized(self):
+        return self._net is not None
+
+    def _initialize(self, interactions):
+        if not self._use_cuda:
+            raise RuntimeError(_NO_CPU)
+        (self._num_users, self._num_items) = (interactions.num_users, interactions.num_items)
+
+        if self._representation is not None:
+            self._net = gpu(self._representation, self._use_cuda)
+        else:
+            self._net = gpu(BilinearNet(self._num_users, self._num_items, self._embedding_dim,
+                                        sparse=self._sparse), self._use_cuda)
+
+        if self._optimizer_func is None:
+            self._optimizer = optim.Adam(self._net.parameters(), weight_decay=self._l2,
+                                         lr=self._learning_rate)
+        else:
+            self._optimizer = self._optimizer_func(self._net.parameters())
+
+        self._loss_func = {'pointwise': pointwise_loss, 'bpr': bpr_loss, 'hinge': hinge_loss,
+                           'adaptive_hinge': adaptive_hinge_loss}[self._loss]
+
+    def _check_input(self, user_ids, item_ids, allow_items_none=False):
+        user_id_max = user_ids if isinstance(user_ids, int) else user_ids.max()
+        if user_id_max >= self._num_users:
+            raise ValueError('Maximum user id greater than number of users in model.')
+        if allow_items_none and item_ids is None:
+            return
+        item_id_max = item_ids if isinstance(item_ids, int) else item_ids.max()
+        if item_id_max >= self._num_items:
+            raise ValueError('Maximum item id greater than number of items in model.')
+
+    # ------------------------------------------------------------------ routes
+
+    def _route(self):
+        net = self._net
+        fusable = isinstance(net, BilinearNet) and net.plain_tables()
+        if fusable and getattr(self._optimizer, 'fused_kind', None) is not None:
+            return 'epoch'
+        if fusable and not self._sparse:
+            return 'fused'
+        return 'generic'
+
+    def _n_neg(self):
+        return self._num_negative_samples if self._loss == 'adaptive_hinge' else 1
+
+    def _device(self):
+        return next(self._net.parameters()).device
+
+    def _epoch_negatives(self, n_interactions):
+        """All of this epoch's negatives in one device draw.
+
+        Consecutive ``randint`` calls consume the masked-rejection stream
+        contiguously, so one draw of ``sum(B_k * n)`` values equals the
+        reference's per-minibatch draws (implicit.py:256-259) concatenated.
+        """
+        return sample_items(self._num_items, n_interactions * self._n_neg(),
+                            random_state=self._random_state, device=self._device())
+
+    def fit(self, interactions, verbose=False):
+        """Fit the model; repeated calls resume from the current weights and
+        optimizer state (implicit.py:184-252)."""
+        user_ids = interactions.user_ids.astype(np.int64)
+        item_ids = interactions.item_ids.astype(np.int64)
+
+        if not self._initialized:
+            self._initialize(interactions)
+        if not self._use_cuda:
+            raise RuntimeError(_NO_CPU)
+
+        self._check_input(user_ids, item_ids)
+        route = self._route()
+
+        for epoch_num in range(self._n_iter):
+            users, items = shuffle(user_ids, item_ids, random_state=self._random_state)
+            user_ids_tensor = gpu(torch.from_numpy(users), self._use_cuda)
+            item_ids_tensor = gpu(torch.from_numpy(items), self._use_cuda)
+            negatives = self._epoch_negatives(len(users))
+
+            if route == 'epoch':
+                epoch_loss = self._fit_epoch_pipeline(user_ids_tensor, item_ids_tensor, negatives)
+            else:
+                epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
+                                                      fused=(route == 'fused'))
+
+            if verbose:
+                print('Epoch {}: loss {}'.format(epoch_num, epoch_loss))
+
+            if np.isnan(epoch_loss) or epoch_loss == 0.0:
+                raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
+
+    def _fit_epoch_pipeline(self, users, items, negatives):
+        """One C call enqueues every minibatch step of the epoch."""
+        net, opt = self._net, self._optimizer
+        lib = _lib.load()
+        n, B, n_neg = users.numel(), int(self._batch_size), self._n_neg()
+        Wu, Wi = net.user_embeddings.weight, net.item_embeddings.weight
+        bu, bi = net.user_biases.weight, net.item_biases.weight
+        dev = Wu.device
+        with torch.no_grad():
+            a = ops.mf_step_args(Wu, Wi, bu, bi, users, items, negatives, self._loss, n_neg,
+                                 batch=min(B, n))
+            rows = lib.slb_mf_compact_rows(a.batch, n_neg, a.loss, 0)
+            D = a.dim
+            urows = torch.empty(rows, dtype=torch.int64, device=dev)
+            irows = torch.empty(rows, dtype=torch.int64, device=dev)
+            gWu = torch.empty((rows, D), dtype=torch.float32, device=dev)
+            gWi = torch.empty((rows, D), dtype=torch.float32, device=dev)
+            gbu = torch.empty(rows, dtype=torch.float32, device=dev)
+            gbi = torch.empty(rows, dtype=torch.float32, device=dev)
+            counts = torch.zeros(2, dtype=torch.int32, device=dev)
+            a.grad_mode = _lib.GRAD_COMPACT
+            a.urows, a.gWu, a.gbu = urows.data_ptr(), gWu.data_ptr(), gbu.data_ptr()
+            a.irows, a.gWi, a.gbi = irows.data_ptr(), gWi.data_ptr(), gbi.data_ptr()
+            a.compact_counts = counts.data_ptr()
+            hp = opt.fused_hparams()
+            a.opt, a.lr, a.weight_decay, a.eps = opt.fused_kind, hp['lr'], hp['weight_decay'], hp['eps']
+            if opt.fused_kind == _lib.OPT_ADAGRAD:
+                states = [opt.fused_state(p) for p in (Wu, Wi, bu, bi)]
+                a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [s.data_ptr() for s in states]
+            need = lib.slb_mf_step_workspace_bytes(a.batch, n_neg, a.loss, a.num_users, a.num_items)
+            ws = ops.workspace('mf%d_%d' % (a.num_users, a.num_items), need, dev)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            n_steps = (n + B - 1) // B
+            losses = torch.empty(n_steps, dtype=torch.float32, device=dev)
+            rc = lib.slb_mf_fit_epoch(ctypes.byref(a), ops._ptr(users), ops._ptr(items),
+                                      ops._ptr(negatives), n, ops._ptr(losses), ops._stream())
+            _lib.check(rc, 'mf_fit_epoch')
+            # the reference averages float(loss.item()) per batch (implicit.py:240,245)
+            host = losses.cpu().numpy().astype(np.float64)
+            if ops.workspace_error_flag(ws):
+                raise ValueError('ids out of range reached the device kernels')
+        return float(host.sum() / n_steps)
+
+    def _fit_epoch_autograd(self, users, items, negatives, fused):
+        net = self._net
+        n_neg = self._n_neg()
+        epoch_loss = torch.zeros((), dtype=torch.float64, device=users.device)
+        lo = 0
+        minibatch_num = -1
+        for minibatch_num, (batch_user, batch_item) in enumerate(
+                minibatch(users, items, batch_size=self._batch_size)):
+            B = batch_user.numel()
+            batch_neg = negatives[lo * n_neg:(lo + B) * n_neg]
+            lo += B
+            self._optimizer.zero_grad()
+            if fused:
+                loss = ops.fused_mf_loss(net.user_embeddings.weight, net.item_embeddings.weight,
+                                         net.user_biases.weight, net.item_biases.weight,
+                                         batch_user, batch_item, batch_neg, self._loss, n_neg)
+            else:
+                positive_prediction = net(batch_user, batch_item)
+                if self._loss == 'adaptive_hinge':
+                    # reference quirk (implicit.py:266-275): users repeat [u0]*n,[u1]*n,..
+                    # but the flat predictions are viewed as (n, B)
+                    rep_users = batch_user.view(B, 1).expand(B, n_neg).reshape(B * n_neg)
+                    negative_prediction = net(rep_users, batch_neg).view(n_neg, B)
+                else:
+                    negative_prediction = net(batch_user, batch_neg)
+                loss = self._loss_func(positive_prediction, negative_prediction)
+            epoch_loss += loss.detach().double()
+            loss.backward()
+            self._optimizer.step()
+        return float(epoch_loss.item()) / (minibatch_num + 1)
+
+    # reference-named helpers (implicit.py:254-275), kept for API parity
+    def _get_negative_prediction(self, user_ids):
+        negative_items = sample_items(self._num_items, len(user_ids),
+                                      random_state=self._random_state, device=user_ids.device)
+        return self._net(user_ids, negative_items)
+
+    def _get_multiple_negative_predictions(self, user_ids, n=5):
+        batch_size = user_ids.size(0)
+        negative_prediction = self._get_negative_prediction(
+            user_ids.view(batch_size, 1).expand(batch_size, n).reshape(batch_size * n))
+        return negative_prediction.view(n, len(user_ids))
+
+    def predict(self, user_ids, item_ids=None):
+        """Scores for (user, item) pairs, or for one user against ``item_ids``
+        (all items when None); returns a NumPy array (implicit.py:277-311)."""
+        self._check_input(user_ids, item_ids, allow_items_none=True)
+        self._net.train(False)
+        user_ids, item_ids = _predict_process_ids(user_ids, item_ids, self._num_items,
+                                                  self._use_cuda)
+        with torch.no_grad():
+            out = self._net(user_ids, item_ids)
+        return cpu(out).detach().numpy().flatten()

@@ -1,0 +1,132 @@
+"""CPU-only tests: host logic, the C-ABI surface, and the no-CPU-fallback rule."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'spotlight_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(slb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from spotlight_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+    loaded = _lib.load()
+    assert loaded.slb_version() == 100
+
+
+def test_struct_layout_matches_header_field_order():
+    from spotlight_b200._lib import MfStepArgs, SeqStepArgs
+    text = open(os.path.join(ROOT, 'include', 'spotlight_b200.h')).read()
+    for cls, tag in ((MfStepArgs, 'slb_mf_step_args'), (SeqStepArgs, 'slb_seq_step_args')):
+        body = text.split('typedef struct %s {' % tag)[1].split('} %s;' % tag)[0]
+        body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+        fields = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(','):
+                name = re.findall(r'([A-Za-z_][A-Za-z0-9_]*)\s*$', part.strip())
+                fields.append(name[0])
+        assert fields == [f[0] for f in cls._fields_], tag
+
+
+def test_no_cpu_path():
+    from spotlight_b200 import ops
+    from spotlight_b200.layers import BloomEmbedding, ScaledEmbedding
+    ids = torch.arange(4)
+    for layer in (ScaledEmbedding(10, 8), BloomEmbedding(100, 8)):
+        with pytest.raises(RuntimeError, match='no CPU path'):
+            layer(ids)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ops.mf_scores(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 1), torch.zeros(4, 1),
+                      ids, ids)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'spotlight_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_layer_parameter_names_and_init():
+    from spotlight_b200.factorization.representations import BilinearNet
+    from spotlight_b200.layers import BloomEmbedding, ScaledEmbedding, ZeroEmbedding
+    net = BilinearNet(30, 20, 16)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert shapes == {'user_embeddings.weight': (30, 16), 'item_embeddings.weight': (20, 16),
+                      'user_biases.weight': (30, 1), 'item_biases.weight': (20, 1)}
+    assert float(ZeroEmbedding(5, 1).weight.abs().sum()) == 0.0
+    e = ScaledEmbedding(2000, 64, padding_idx=0)
+    assert float(e.weight[0].abs().sum()) == 0.0
+    assert abs(float(e.weight[1:].std()) - 1.0 / 64) < 2e-3          # std 1/D, not 1/sqrt(D)
+    b = BloomEmbedding(1000, 8, compression_ratio=0.25, num_hash_functions=3)
+    assert b.compressed_num_embeddings == 250 and tuple(b.embeddings.weight.shape) == (250, 8)
+    with pytest.raises(ValueError):
+        BloomEmbedding(10, 4, num_hash_functions=25)
+    with pytest.raises(NotImplementedError):
+        BloomEmbedding(10, 4, bag=True)
+
+
+def test_interactions_and_to_sequence():
+    from spotlight_b200.interactions import Interactions
+    g = load_golden('to_sequence')
+    it = Interactions(g['users'], g['items'], timestamps=g['ts'])
+    for tag, kw in [('a', dict(max_sequence_length=7)),
+                    ('b', dict(max_sequence_length=5, step_size=1)),
+                    ('c', dict(max_sequence_length=6, min_sequence_length=3, step_size=2))]:
+        s = it.to_sequence(**kw)
+        assert s.sequences.dtype == np.int32
+        assert (s.sequences == g['seq_' + tag]).all() and (s.user_ids == g['uid_' + tag]).all()
+    # the reference's two known-answer cases (tests/test_interactions.py:67-100)
+    it = Interactions(np.zeros(5), np.arange(5) + 1, timestamps=np.arange(5))
+    assert (it.to_sequence(max_sequence_length=5, step_size=1).sequences == np.array(
+        [[1, 2, 3, 4, 5], [0, 1, 2, 3, 4], [0, 0, 1, 2, 3], [0, 0, 0, 1, 2], [0, 0, 0, 0, 1]])).all()
+    assert (it.to_sequence(max_sequence_length=5, step_size=2).sequences == np.array(
+        [[1, 2, 3, 4, 5], [0, 0, 1, 2, 3], [0, 0, 0, 0, 1]])).all()
+    with pytest.raises(ValueError):
+        Interactions(np.arange(3), np.arange(3), num_users=2)
+    with pytest.raises(ValueError):
+        Interactions(np.arange(3), np.arange(3)).to_sequence()          # no timestamps
+    assert it.tocsr().shape == (1, 6)
+
+
+def test_shuffle_and_minibatch_follow_the_stream():
+    from spotlight_b200.torch_utils import minibatch, shuffle
+    a, b = np.arange(100), np.arange(100) * 2
+    r1, r2 = np.random.RandomState(3), np.random.RandomState(3)
+    sa, sb = shuffle(a, b, random_state=r1)
+    order = np.arange(100)
+    r2.shuffle(order)
+    assert (sa == a[order]).all() and (sb == b[order]).all()
+    assert r1.get_state()[2] == r2.get_state()[2]
+    chunks = list(minibatch(torch.arange(10), torch.arange(10), batch_size=4))
+    assert [len(c[0]) for c in chunks] == [4, 4, 2]
+    with pytest.raises(ValueError):
+        shuffle(a, b[:5])
+
+
+def test_sample_items_host_path_is_numpy():
+    from spotlight_b200.sampling import sample_items
+    r1, r2 = np.random.RandomState(9), np.random.RandomState(9)
+    assert (sample_items(1683, (4, 5), r1) == r2.randint(0, 1683, (4, 5), dtype=np.int64)).all()

@@ -1,0 +1,283 @@
+"""GPU parity tests for the matrix-factorisation hot path: the CUDA kernels
+(reached through the C-ABI) against the committed golden vectors of the live
+reference, against the oracle on seeded inputs, and -- at benchmark sizes --
+through size-independent properties (bit-reproducibility, conservation sums,
+agreement with an fp32 ATen restatement).
+
+Tolerance: integer work (sampling, hashing, row indexing) bit-exact; floating
+point 1e-5 relative to the tensor's max magnitude (north star).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from oracle import mf as omf
+
+pytestmark = pytest.mark.gpu
+
+LOSS_OF = {'mf_pointwise': 'pointwise', 'mf_bpr': 'bpr', 'mf_hinge': 'hinge',
+           'mf_adaptive_hinge': 'adaptive_hinge', 'mf_bpr_d64': 'bpr'}
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev())
+
+
+# ------------------------------------------------------------------ sampler
+
+@pytest.mark.parametrize('num_items,shape', [(100000, 70000), (1683, (5, 77)), (1000000, 1234),
+                                             (50000000, 999), (1, 5), (2, 7), (4096, 3000),
+                                             (4097, 3000), (100000, 1), (100000, 2_000_003)])
+def test_sampler_bit_exact(num_items, shape):
+    from spotlight_b200.sampling import sample_items
+    a, b = np.random.RandomState(123), np.random.RandomState(123)
+    a.randint(0, 10, 77)
+    b.randint(0, 10, 77)          # start mid-block
+    want = a.randint(0, num_items, shape, dtype=np.int64)
+    got = sample_items(num_items, shape, random_state=b, device=dev())
+    assert got.dtype == torch.int64 and tuple(got.shape) == want.shape
+    assert (got.cpu().numpy() == want).all()
+    sa, sb = a.get_state(), b.get_state()
+    assert (sa[1] == sb[1]).all() and sa[2] == sb[2]
+    # and the stream continues identically on the host
+    assert (a.randint(0, 1000, 50) == b.randint(0, 1000, 50)).all()
+
+
+def test_sampler_golden_stream():
+    from spotlight_b200.sampling import sample_items
+    g = load_golden('rng_stream')
+    rs = np.random.RandomState(42)
+    assert rs.randint(-10**8, 10**8) == int(g['ctor'])
+    idx = np.arange(1000)
+    rs.shuffle(idx)
+    for key, (n, sz) in zip(['n0', 'n1', 'n2', 'n3', 'n4'],
+                            [(100000, 257), (1683, 64), (1000000, 100), (50000000, 33),
+                             (1683, (5, 7))]):
+        got = sample_items(n, sz, random_state=rs, device=dev())
+        assert (got.cpu().numpy() == g[key]).all(), key
+    st = rs.get_state()
+    assert (st[1] == g['end_key']).all() and st[2] == int(g['end_pos'])
+
+
+# --------------------------------------------------------------- fused step
+
+def _params(g):
+    return (t(g['sd.user_embeddings.weight']), t(g['sd.item_embeddings.weight']),
+            t(g['sd.user_biases.weight']), t(g['sd.item_biases.weight']))
+
+
+@pytest.mark.parametrize('name', sorted(LOSS_OF))
+def test_fused_step_golden(name):
+    from spotlight_b200 import ops
+    from spotlight_b200._lib import LOSS_KIND
+    g = load_golden(name)
+    loss = LOSS_OF[name]
+    n_neg = int(g['n_neg']) if loss == 'adaptive_hinge' else 1
+    Wu, Wi, bu, bi = _params(g)
+    out = ops.mf_train_step(Wu, Wi, bu, bi, t(g['users']), t(g['items']), t(g['negs']),
+                            LOSS_KIND[loss], n_neg, True)
+    l, pos, neg, dWu, dWi, dbu, dbi = [o.cpu().numpy() for o in out]
+    assert_close(pos, g['pos'], 1e-5, what='pos')
+    assert_close(neg.reshape(g['neg'].shape), g['neg'], 1e-5, what='neg')
+    assert_close(l, g['loss'], 1e-5, what='loss')
+    assert_close(dWu, g['grad.user_embeddings.weight'], 1e-5, what='dWu')
+    assert_close(dWi, g['grad.item_embeddings.weight'], 1e-5, what='dWi')
+    assert_close(dbu, g['grad.user_biases.weight'], 1e-5, atol=1e-7, what='dbu')
+    assert_close(dbi, g['grad.item_biases.weight'], 1e-5, what='dbi')
+    # untouched rows are exactly zero, like the reference's dense grad
+    ref_zero = np.abs(g['grad.item_embeddings.weight']).sum(1) == 0
+    assert np.all(dWi[ref_zero] == 0)
+
+
+@pytest.mark.parametrize('loss', ['pointwise', 'bpr', 'hinge', 'adaptive_hinge'])
+@pytest.mark.parametrize('dim', [4, 8, 24, 128, 256])
+def test_fused_step_vs_oracle_dims(loss, dim):
+    from spotlight_b200 import ops
+    from spotlight_b200._lib import LOSS_KIND
+    rs = np.random.RandomState(dim)
+    U, I, B, n_neg = 211, 97, 777, (3 if loss == 'adaptive_hinge' else 1)
+    Wu = (rs.randn(U, dim) * 0.3).astype(np.float32)
+    Wi = (rs.randn(I, dim) * 0.3).astype(np.float32)
+    bu = (rs.randn(U, 1) * 0.1).astype(np.float32)
+    bi = (rs.randn(I, 1) * 0.1).astype(np.float32)
+    users = rs.randint(0, U, B).astype(np.int64)
+    items = rs.randint(0, I, B).astype(np.int64)
+    negs = rs.randint(0, I, B * n_neg).astype(np.int64)
+    ref = omf.mf_step(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, np.float64)
+    out = ops.mf_train_step(t(Wu), t(Wi), t(bu), t(bi), t(users), t(items), t(negs),
+                            LOSS_KIND[loss], n_neg, True)
+    l, pos, neg, dWu, dWi, dbu, dbi = [o.cpu().numpy() for o in out]
+    assert_close(pos, ref['pos'], 1e-5, what='pos')
+    assert_close(neg.reshape(ref['neg'].shape), ref['neg'], 1e-5, what='neg')
+    assert_close(l, ref['loss'], 1e-5, what='loss')
+    assert_close(dWu, ref['dWu'], 1e-5, what='dWu')
+    assert_close(dWi, ref['dWi'], 1e-5, what='dWi')
+    assert_close(dbu, ref['dbu'], 1e-5, atol=1e-7, what='dbu')
+    assert_close(dbi, ref['dbi'], 1e-5, what='dbi')
+
+
+def test_fused_step_hot_rows_and_batch_of_one():
+    """Heavy duplication (every interaction hits the same few rows: the
+    long-segment path) and the batch-of-one case the reference cannot run."""
+    from spotlight_b200 import ops
+    rs = np.random.RandomState(1)
+    U, I, D, B = 5, 3, 32, 4000
+    Wu = (rs.randn(U, D) * 0.3).astype(np.float32)
+    Wi = (rs.randn(I, D) * 0.3).astype(np.float32)
+    bu = np.zeros((U, 1), np.float32)
+    bi = np.zeros((I, 1), np.float32)
+    users = rs.randint(0, U, B).astype(np.int64)
+    items = rs.randint(0, I, B).astype(np.int64)
+    negs = rs.randint(0, I, B).astype(np.int64)
+    ref = omf.mf_step(Wu, Wi, bu, bi, users, items, negs, 'bpr', 1, np.float64)
+    out = ops.mf_train_step(t(Wu), t(Wi), t(bu), t(bi), t(users), t(items), t(negs), 1, 1, False)
+    assert_close(out[3].cpu().numpy(), ref['dWu'], 1e-5, what='dWu hot')
+    assert_close(out[4].cpu().numpy(), ref['dWi'], 1e-5, what='dWi hot')
+    ref1 = omf.mf_step(Wu, Wi, bu, bi, users[:1], items[:1], negs[:1], 'hinge', 1, np.float64)
+    out1 = ops.mf_train_step(t(Wu), t(Wi), t(bu), t(bi), t(users[:1]), t(items[:1]), t(negs[:1]),
+                             2, 1, False)
+    assert_close(out1[0].cpu().numpy(), ref1['loss'], 1e-5, what='loss b1')
+    assert_close(out1[3].cpu().numpy(), ref1['dWu'], 1e-5, what='dWu b1')
+
+
+def test_fused_step_full_size_properties():
+    """BASELINE config 2 shape (1M users x 100K items x 64, B = 65536):
+    bit-reproducible, conservation identities, and agreement with an fp32 ATen
+    restatement of the same step."""
+    from spotlight_b200 import ops
+    torch.manual_seed(0)
+    U, I, D, B = 1_000_000, 100_000, 64, 65536
+    d = dev()
+    Wu = torch.randn(U, D, device=d) / D
+    Wi = torch.randn(I, D, device=d) / D
+    bu = torch.randn(U, 1, device=d) * 0.01
+    bi = torch.randn(I, 1, device=d) * 0.01
+    users = torch.randint(0, U, (B,), device=d)
+    items = torch.randint(0, I, (B,), device=d)
+    negs = torch.randint(0, I, (B,), device=d)
+    o1 = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 1, 1, True)
+    o2 = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 1, 1, True)
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b), 'fused step is not bit-reproducible'
+    loss, pos, neg, dWu, dWi, dbu, dbi = o1
+    # ATen fp32 restatement
+    u, qi, qj = Wu[users], Wi[items], Wi[negs]
+    p = (u * qi).sum(1) + bu[users, 0] + bi[items, 0]
+    n = (u * qj).sum(1) + bu[users, 0] + bi[negs, 0]
+    s = torch.sigmoid(p - n)
+    assert_close(pos.cpu().numpy(), p.cpu().numpy(), 1e-5, what='pos')
+    assert_close(loss.item(), (1 - s).mean().item(), 1e-5, what='loss')
+    gp = -(s * (1 - s)) / B
+    rWu = torch.zeros_like(Wu).index_add_(0, users, gp[:, None] * (qi - qj))
+    rWi = torch.zeros_like(Wi).index_add_(0, items, gp[:, None] * u).index_add_(0, negs, -gp[:, None] * u)
+    assert_close(dWu.cpu().numpy(), rWu.cpu().numpy(), 1e-5, what='dWu')
+    assert_close(dWi.cpu().numpy(), rWi.cpu().numpy(), 2e-5, what='dWi')
+    # conservation: bpr gives gp + gn = 0 per interaction
+    assert abs(dbi.double().sum().item()) < 1e-6
+    assert torch.count_nonzero(dbu).item() == 0 or dbu.abs().max().item() < 1e-9
+
+
+# -------------------------------------------------------- scores / embedding
+
+def test_mf_scores_forward_backward_vs_autograd():
+    from spotlight_b200 import ops
+    rs = np.random.RandomState(4)
+    U, I, D, B = 50, 40, 32, 300
+    Wu = t((rs.randn(U, D) * 0.3).astype(np.float32)).requires_grad_()
+    Wi = t((rs.randn(I, D) * 0.3).astype(np.float32)).requires_grad_()
+    bu = t((rs.randn(U, 1) * 0.1).astype(np.float32)).requires_grad_()
+    bi = t((rs.randn(I, 1) * 0.1).astype(np.float32)).requires_grad_()
+    users = t(rs.randint(0, U, B).astype(np.int64))
+    items = t(rs.randint(0, I, B).astype(np.int64))
+    w = t(rs.randn(B).astype(np.float32))
+    (ops.mf_scores(Wu, Wi, bu, bi, users, items) * w).sum().backward()
+    got = [p.grad.clone() for p in (Wu, Wi, bu, bi)]
+    for p in (Wu, Wi, bu, bi):
+        p.grad = None
+    ref = (Wu[users] * Wi[items]).sum(1) + bu[users, 0] + bi[items, 0]
+    (ref * w).sum().backward()
+    for a, p, nm in zip(got, (Wu, Wi, bu, bi), 'Wu Wi bu bi'.split()):
+        assert_close(a.cpu().numpy(), p.grad.cpu().numpy(), 1e-5, what=nm)
+    # one user broadcast over all items (predict path)
+    one = ops.mf_scores(Wu, Wi, bu, bi, users[:1], torch.arange(I, device=dev()))
+    ref1 = (Wu[users[:1]] * Wi).sum(1) + bu[users[0], 0] + bi[:, 0]
+    assert_close(one.detach().cpu().numpy(), ref1.detach().cpu().numpy(), 1e-5, what='bcast')
+
+
+@pytest.mark.parametrize('name', ['mf_hinge_bloom', 'mf_adaptive_bloom'])
+def test_bloom_rows_bit_exact(name):
+    from spotlight_b200.layers import BloomEmbedding
+    g = load_golden(name)
+    layer = BloomEmbedding(int(g['num_items']), int(g['dim']),
+                           compression_ratio=float(g['bloom_ratio']),
+                           num_hash_functions=int(g['bloom_H'])).to(dev())
+    rows = layer._get_hashed_indices(t(g['items'])).cpu().numpy()
+    assert (rows == g['bloom_rows_items']).all()
+    big = np.random.RandomState(0).randint(0, 50_000_000, 20000).astype(np.int64)
+    big[:3] = [0, 49_999_999, 2**31 - 1]
+    from spotlight_b200 import ops
+    from oracle.murmur import bloom_rows, SEEDS
+    got = ops.bloom_rows(t(big), SEEDS[:4], 1_000_000, 0).cpu().numpy()
+    assert (got == bloom_rows(big, 4, 1_000_000)).all()
+
+
+@pytest.mark.parametrize('name,loss', [('mf_hinge_bloom', 'hinge'),
+                                       ('mf_adaptive_bloom', 'adaptive_hinge')])
+def test_generic_route_bloom_golden(name, loss):
+    """BilinearNet with a BloomEmbedding item layer through the generic
+    (gather op + loss op + autograd) route vs the reference's grads."""
+    from spotlight_b200.factorization.representations import BilinearNet
+    from spotlight_b200.layers import BloomEmbedding, ScaledEmbedding
+    from spotlight_b200 import losses
+    g = load_golden(name)
+    U, I, D = int(g['num_users']), int(g['num_items']), int(g['dim'])
+    net = BilinearNet(U, I, D, user_embedding_layer=ScaledEmbedding(U, D),
+                      item_embedding_layer=BloomEmbedding(
+                          I, D, compression_ratio=float(g['bloom_ratio']),
+                          num_hash_functions=int(g['bloom_H'])))
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')})
+    net = net.to(dev())
+    users, items, negs = t(g['users']), t(g['items']), t(g['negs'])
+    B = users.numel()
+    pos = net(users, items)
+    if loss == 'adaptive_hinge':
+        n = int(g['n_neg'])
+        rep = users.view(B, 1).expand(B, n).reshape(B * n)
+        neg = net(rep, negs).view(n, B)
+        l = losses.adaptive_hinge_loss(pos, neg)
+    else:
+        neg = net(users, negs)
+        l = losses.hinge_loss(pos, neg)
+    l.backward()
+    assert_close(pos.detach().cpu().numpy(), g['pos'], 1e-5, what='pos')
+    assert_close(neg.detach().cpu().numpy(), g['neg'], 1e-5, what='neg')
+    assert_close(l.item(), g['loss'], 1e-5, what='loss')
+    for k, p in net.named_parameters():
+        assert_close(p.grad.cpu().numpy(), g['grad.' + k], 1e-5, atol=1e-7, what=k)
+
+
+# ------------------------------------------------------------------- losses
+
+@pytest.mark.parametrize('kind', ['pointwise', 'bpr', 'hinge', 'adaptive_hinge'])
+@pytest.mark.parametrize('masked', [False, True])
+def test_loss_ops_vs_oracle(kind, masked):
+    from spotlight_b200 import losses
+    rs = np.random.RandomState(2)
+    shape = (37, 11)
+    pos = rs.randn(*shape).astype(np.float32)
+    neg = rs.randn(*((4,) + shape if kind == 'adaptive_hinge' else shape)).astype(np.float32)
+    mask = (rs.rand(*shape) > 0.3) if masked else None
+    lref, gp, gn = omf.loss_and_score_grads(kind, pos, neg, mask, np.float64)
+    p, n = t(pos).requires_grad_(), t(neg).requires_grad_()
+    fn = getattr(losses, kind + '_loss')
+    l = fn(p, n, mask=t(mask) if masked else None)
+    l.backward()
+    assert_close(l.item(), lref, 1e-5, what='loss')
+    assert_close(p.grad.cpu().numpy(), gp, 1e-5, what='gpos')
+    assert_close(n.grad.cpu().numpy(), gn, 1e-5, what='gneg')
