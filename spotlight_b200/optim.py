@@ -59,11 +59,22 @@ class FusedAdagrad(torch.optim.Adagrad):
         return self.state[param]['sum']
 
 
+class _Factory(object):
+    """Picklable ``optimizer_func`` (models are saved whole with ``torch.save``)."""
+
+    def __init__(self, cls, **kwargs):
+        self.cls = cls
+        self.kwargs = kwargs
+
+    def __call__(self, params):
+        return self.cls(params, **self.kwargs)
+
+
 def fused_sgd(lr=1e-2, weight_decay=0.0):
     """``optimizer_func`` factory for :class:`FusedSGD`."""
-    return lambda params: FusedSGD(params, lr=lr, weight_decay=weight_decay)
+    return _Factory(FusedSGD, lr=lr, weight_decay=weight_decay)
 
 
 def fused_adagrad(lr=1e-2, weight_decay=0.0, eps=1e-10):
     """``optimizer_func`` factory for :class:`FusedAdagrad`."""
-    return lambda params: FusedAdagrad(params, lr=lr, weight_decay=weight_decay, eps=eps)
+    return _Factory(FusedAdagrad, lr=lr, weight_decay=weight_decay, eps=eps)

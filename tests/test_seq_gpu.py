@@ -1,0 +1,134 @@
+"""GPU parity tests for the sequence hot path (PoolNet, CNNNet) against the
+live reference's golden vectors and the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from oracle import seq as oseq
+
+pytestmark = pytest.mark.gpu
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to('cuda:0')
+
+
+def _cnn_spec(g):
+    L = int(g['cnn.num_layers'])
+    kw = np.atleast_1d(g['cnn.kernel_width'])
+    dl = np.atleast_1d(g['cnn.dilation'])
+    return dict(kernel_width=[int(kw[i % len(kw)]) for i in range(L)],
+                dilation=[int(dl[i % len(dl)]) for i in range(L)],
+                nonlinearity=str(g['cnn.nonlinearity']) if 'cnn.nonlinearity' in g else 'tanh',
+                residual=bool(g['cnn.residual_connections']) if 'cnn.residual_connections' in g else True,
+                weights=[t(g['sd.cnn_%d.weight' % i]) for i in range(L)],
+                biases=[t(g['sd.cnn_%d.bias' % i]) for i in range(L)])
+
+
+@pytest.mark.parametrize('name', ['pool_pointwise', 'pool_bpr', 'pool_hinge', 'pool_adaptive_hinge'])
+def test_pool_step_golden(name):
+    from spotlight_b200 import ops
+    g = load_golden(name)
+    loss = name.split('_', 1)[1]
+    n_neg = int(g['n_neg']) if loss == 'adaptive_hinge' else 1
+    out = ops.seq_train_step(t(g['sd.item_embeddings.weight']), t(g['sd.item_biases.weight']),
+                             t(g['seqs']), t(g['negs']), loss, n_neg, None, want_scores=True)
+    assert_close(out['pos'].cpu().numpy(), g['pos'], 1e-5, what='pos')
+    assert_close(out['neg'].cpu().numpy().reshape(g['neg'].shape), g['neg'], 1e-5, what='neg')
+    assert_close(out['loss'].item(), g['loss'], 1e-5, what='loss')
+    assert_close(out['dE'].cpu().numpy(), g['grad.item_embeddings.weight'], 1e-5, what='dE')
+    assert_close(out['dbias'].cpu().numpy(), g['grad.item_biases.weight'], 1e-5, what='dbias')
+    assert float(out['dE'][0].abs().sum()) == 0.0
+    rep = ops.seq_representation(t(g['sd.item_embeddings.weight']), t(g['seqs']), None)
+    assert_close(rep[:, -1].cpu().numpy(), g['final'], 1e-5, what='final')
+    assert_close(rep[:, :-1].permute(0, 2, 1).cpu().numpy(), g['user_rep'], 1e-5, what='user_rep')
+
+
+@pytest.mark.parametrize('name,loss', [('cnn_pointwise', 'pointwise'), ('cnn_bpr_l2_relu', 'bpr'),
+                                       ('cnn_adaptive_k5_nores', 'adaptive_hinge')])
+def test_cnn_step_golden(name, loss):
+    from spotlight_b200 import ops
+    g = load_golden(name)
+    n_neg = int(g['n_neg']) if loss == 'adaptive_hinge' else 1
+    spec = _cnn_spec(g)
+    out = ops.seq_train_step(t(g['sd.item_embeddings.weight']), t(g['sd.item_biases.weight']),
+                             t(g['seqs']), t(g['negs']), loss, n_neg, spec, want_scores=True)
+    assert_close(out['pos'].cpu().numpy(), g['pos'], 1e-5, what='pos')
+    assert_close(out['neg'].cpu().numpy().reshape(g['neg'].shape), g['neg'], 1e-5, what='neg')
+    assert_close(out['loss'].item(), g['loss'], 1e-5, what='loss')
+    assert_close(out['dE'].cpu().numpy(), g['grad.item_embeddings.weight'], 1e-5, what='dE')
+    assert_close(out['dbias'].cpu().numpy(), g['grad.item_biases.weight'], 1e-5, what='dbias')
+    for i in range(len(spec['weights'])):
+        assert_close(out['dconv_w'][i].cpu().numpy(), g['grad.cnn_%d.weight' % i], 1e-5, what='dW%d' % i)
+        assert_close(out['dconv_b'][i].cpu().numpy(), g['grad.cnn_%d.bias' % i], 1e-5, what='db%d' % i)
+    rep = ops.seq_representation(t(g['sd.item_embeddings.weight']), t(g['seqs']), spec)
+    assert_close(rep[:, -1].cpu().numpy(), g['final'], 1e-5, what='final')
+
+
+@pytest.mark.parametrize('kind', ['pool', 'cnn'])
+@pytest.mark.parametrize('D,S,B', [(128, 200, 16), (64, 33, 40), (256, 7, 9)])
+def test_seq_step_vs_oracle_sizes(kind, D, S, B):
+    from spotlight_b200 import ops
+    rs = np.random.RandomState(D + S)
+    I = 500
+    E = (rs.randn(I, D) * 0.2).astype(np.float32)
+    E[0] = 0
+    bias = (rs.randn(I, 1) * 0.1).astype(np.float32)
+    bias[0] = 0
+    seqs = rs.randint(1, I, (B, S)).astype(np.int64)
+    for b in range(0, B, 2):
+        seqs[b, :rs.randint(0, S)] = 0
+    negs = rs.randint(0, I, (B, S)).astype(np.int64)
+    spec, convs = None, None
+    if kind == 'cnn':
+        W = [(rs.randn(D, D, 3, 1) * 0.05).astype(np.float32), (rs.randn(D, D, 2, 1) * 0.05).astype(np.float32)]
+        bb = [(rs.randn(D) * 0.05).astype(np.float32) for _ in W]
+        convs = list(zip(W, bb))
+        spec = dict(kernel_width=[3, 2], dilation=[1, 2], nonlinearity='tanh', residual=True,
+                    weights=[t(w) for w in W], biases=[t(x) for x in bb])
+        ref = oseq.cnn_step(E, bias, convs, seqs, negs, [3, 2], [1, 2], 'bpr', 1, 'tanh', True, np.float64)
+    else:
+        ref = oseq.pool_step(E, bias, seqs, negs, 'bpr', 1, np.float64)
+    out = ops.seq_train_step(t(E), t(bias), t(seqs), t(negs), 'bpr', 1, spec, want_scores=True)
+    assert_close(out['pos'].cpu().numpy(), ref['pos'], 2e-5, what='pos')
+    assert_close(out['loss'].item(), ref['loss'], 1e-5, what='loss')
+    assert_close(out['dE'].cpu().numpy(), ref['dE'], 2e-5, what='dE')
+    assert_close(out['dbias'].cpu().numpy(), ref['dbias'], 2e-5, what='dbias')
+    if kind == 'cnn':
+        for i in range(2):
+            assert_close(out['dconv_w'][i].cpu().numpy(), ref['dconvs'][i][0], 2e-5, what='dW')
+            assert_close(out['dconv_b'][i].cpu().numpy(), ref['dconvs'][i][1], 2e-5, what='db')
+    out2 = ops.seq_train_step(t(E), t(bias), t(seqs), t(negs), 'bpr', 1, spec)
+    assert torch.equal(out['dE'], out2['dE']), 'sequence step is not bit-reproducible'
+
+
+@pytest.mark.parametrize('name,loss,rep', [('fit_pool_hinge', 'hinge', 'pooling'),
+                                           ('fit_cnn_pointwise', 'pointwise', 'cnn')])
+def test_sequence_model_fit_golden(name, loss, rep, capsys):
+    from spotlight_b200.interactions import SequenceInteractions
+    from spotlight_b200.sequence.implicit import ImplicitSequenceModel
+    g = load_golden(name)
+    inter = SequenceInteractions(g['seqs'], num_items=int(g['num_items']))
+    model = ImplicitSequenceModel(loss=loss, representation=rep, embedding_dim=int(g['dim']),
+                                  batch_size=int(g['batch']), n_iter=int(g['n_iter']),
+                                  optimizer_func=lambda p: torch.optim.SGD(p, lr=0.5), use_cuda=True,
+                                  random_state=np.random.RandomState(int(g['seed'])))
+    model._initialize(inter)
+    model._net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('init.')})
+    assert model._route() == 'fused'
+    model.fit(inter, verbose=True)
+    lines = [l for l in capsys.readouterr().out.strip().split('\n') if l.startswith('Epoch')]
+    losses = np.array([float(l.split('loss')[1]) for l in lines])
+    assert_close(losses, g['epoch_losses'], 1e-5, what='epoch losses')
+    for k, v in model._net.state_dict().items():
+        assert_close(v.cpu().numpy(), g['final.' + k], 1e-4, atol=1e-7, what=k)
+    st = model._random_state.get_state()
+    assert (st[1] == g['rs_key']).all() and st[2] == int(g['rs_pos'])
+    assert_close(model.predict(g['seqs'][1]), g['predict'], 1e-4, what='predict')
+
+
+def test_generic_route_pool_bloom_golden():
+    """PoolNet over a BloomEmbedding through the generic autograd route."""
+    pytest.skip('generic sequence route needs a differentiable user_representation (next round)')
