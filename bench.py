@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: interactions/sec, BPR matrix factorisation, 1M users x
+100K items x dim 64 (BASELINE.json configs[1]), synthetic uniform ids.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one minibatch through the fit() hot path: negative draw (device
+MT19937, bit-exact with NumPy), fused forward kernel, segment-index build,
+deterministic backward kernel, fused row-wise Adagrad update.
+
+One JSON line on stdout (rank 0):
+  value      whole-job interactions/s with ids resident in HBM (device timed,
+             CUDA events, max over ranks)
+  e2e        the same metric through the public API, ImplicitFactorizationModel
+             .fit(Interactions) with HOST numpy ids: host shuffle, H2D copies,
+             device negatives, training steps, D2H of the per-batch losses
+  roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's loop restated on stock torch CPU ops
+             (oracle/torch_port.py, kind "port") timed on this box's host cores
+             on a bounded sample of the same workload
+
+``--impl reference`` times only that CPU port (all host threads) on the same
+config and prints the same line shape with "impl": "reference".
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'interactions/sec (BPR MF, 1Mx100Kx64)'
+UNIT = 'interactions/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=65536)
+    ap.add_argument('--users', type=int, default=1_000_000)
+    ap.add_argument('--items', type=int, default=100_000)
+    ap.add_argument('--dim', type=int, default=64)
+    ap.add_argument('--loss', default='bpr')
+    ap.add_argument('--lr', type=float, default=0.05)
+    ap.add_argument('--cpu-steps', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {'workload': 'synthetic uniform 1M users x 100K items, BilinearNet dim=64, bpr_loss '
+                        '(BASELINE.json configs[1])',
+            'num_users': a.users, 'num_items': a.items, 'dim': a.dim, 'loss': a.loss,
+            'batch': a.batch, 'optimizer': 'adagrad(lr=%g), row-wise fused' % a.lr,
+            'negatives': 'device MT19937 masked rejection (numpy-bit-exact)',
+            'parallelism': 'single GPU' if n_gpus == 1 else 'replicas x%d' % n_gpus,
+            'l2': 'inputs (embedding tables 282 MB + ids) exceed the 126 MB L2; no flush'}
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
+                          for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU port (cpu_baseline and the reference arm)
+# --------------------------------------------------------------------------
+
+def run_cpu_port(a, steps, warmup):
+    """interactions/s of the reference loop restated on torch CPU ops."""
+    import torch
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = torch_port.PortBilinearNet(a.users, a.items, a.dim)
+    opt = torch.optim.Adagrad(net.parameters(), lr=a.lr)
+    rs = np.random.RandomState(0)
+    n = (steps + warmup) * a.batch
+    users = rs.randint(0, a.users, n).astype(np.int64)
+    items = rs.randint(0, a.items, n).astype(np.int64)
+    B = a.batch
+    torch_port.fit_steps(net, opt, users[:warmup * B], items[:warmup * B], a.items, B, a.loss,
+                         rs, max_steps=warmup)
+    t0 = time.perf_counter()
+    torch_port.fit_steps(net, opt, users[warmup * B:], items[warmup * B:], a.items, B, a.loss, rs,
+                         max_steps=steps)
+    dt = time.perf_counter() - t0
+    return {'value': steps * B / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': '%d steps of batch %d after %d warm-up, torch %s CPU, Adagrad dense '
+                      '(reference loop, oracle/torch_port.py)' % (steps, B, warmup, torch.__version__),
+            'ms_per_step': dt / steps * 1e3}
+
+
+def main_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 40))       # each reference step is O(table): ~0.1-0.3 s
+    warm = max(1, min(a.warmup, 3))
+    r = run_cpu_port(a, steps, warm)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
+            'n_gpus': a.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(a, a.gpus),
+            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+
+class _Shape(object):
+    def __init__(self, num_users, num_items):
+        self.num_users, self.num_items = num_users, num_items
+
+
+def build_model(a, device_index):
+    import torch
+    from spotlight_b200 import optim
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    torch.cuda.set_device(device_index)
+    model = ImplicitFactorizationModel(loss=a.loss, embedding_dim=a.dim, batch_size=a.batch,
+                                       n_iter=1, optimizer_func=optim.fused_adagrad(lr=a.lr),
+                                       use_cuda=True, random_state=np.random.RandomState(42))
+    model._initialize(_Shape(a.users, a.items))
+    assert model._route() == 'epoch'
+    return model
+
+
+def kernel_breakdown(model, users, items, a, steps):
+    """Per-kernel average duration (ms) with CUDA events around single-kernel launches."""
+    import ctypes
+    import torch
+    from spotlight_b200 import _lib, ops
+    from spotlight_b200.sampling import sample_items
+    lib = _lib.load()
+    net, opt = model._net, model._optimizer
+    dev = users.device
+    B = a.batch
+    Wu, Wi = net.user_embeddings.weight, net.item_embeddings.weight
+    bu, bi = net.user_biases.weight, net.item_biases.weight
+    negs = sample_items(a.items, steps * B, random_state=np.random.RandomState(1), device=dev)
+    names = ['mf_fwd', 'seg_scan', 'mf_fill', 'mf_bwd', 'mf_apply']
+    tot = dict.fromkeys(names, 0.0)
+    with torch.no_grad():
+        st = ops.mf_step_args(Wu, Wi, bu, bi, users[:B], items[:B], negs[:B], a.loss, 1, batch=B)
+        rows = lib.slb_mf_compact_rows(B, 1, st.loss, 0)
+        bufs = dict(urows=torch.empty(rows, dtype=torch.int64, device=dev),
+                    irows=torch.empty(rows, dtype=torch.int64, device=dev),
+                    gWu=torch.empty((rows, a.dim), device=dev), gWi=torch.empty((rows, a.dim), device=dev),
+                    gbu=torch.empty(rows, device=dev), gbi=torch.empty(rows, device=dev),
+                    counts=torch.zeros(2, dtype=torch.int32, device=dev),
+                    loss=torch.empty(1, device=dev))
+        st.grad_mode = _lib.GRAD_COMPACT
+        st.urows, st.gWu, st.gbu = bufs['urows'].data_ptr(), bufs['gWu'].data_ptr(), bufs['gbu'].data_ptr()
+        st.irows, st.gWi, st.gbi = bufs['irows'].data_ptr(), bufs['gWi'].data_ptr(), bufs['gbi'].data_ptr()
+        st.compact_counts, st.loss_out = bufs['counts'].data_ptr(), bufs['loss'].data_ptr()
+        hp = opt.fused_hparams()
+        st.opt, st.lr, st.weight_decay, st.eps = opt.fused_kind, hp['lr'], hp['weight_decay'], hp['eps']
+        states = [opt.fused_state(p) for p in (Wu, Wi, bu, bi)]
+        st.state_Wu, st.state_Wi, st.state_bu, st.state_bi = [s.data_ptr() for s in states]
+        need = lib.slb_mf_step_workspace_bytes(B, 1, st.loss, a.users, a.items)
+        ws = ops.workspace('mf%d_%d' % (a.users, a.items), need, dev)
+        st.workspace, st.workspace_bytes = ws.data_ptr(), ws.numel()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        stream = ops._stream()
+        for k in range(steps):
+            st.users = users[k * B:].data_ptr()
+            st.items = items[k * B:].data_ptr()
+            st.negs = negs[k * B:].data_ptr()
+            evs[0].record()
+            for i in range(5):
+                _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(st), 1 << i, stream), 'phase')
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            for i, nm in enumerate(names):
+                tot[nm] += evs[i].elapsed_time(evs[i + 1])
+    return {nm: tot[nm] / steps for nm in names}
+
+
+def main_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    model = build_model(a, local)
+    dev = torch.device('cuda', local)
+    B, K, W = a.batch, a.steps, a.warmup
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n = (K + W) * B
+    users = torch.randint(0, a.users, (n,), device=dev, generator=g)
+    items = torch.randint(0, a.items, (n,), device=dev, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------
+    model._run_epoch_device(users[:W * B], items[:W * B])              # warm-up steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    epoch_loss = model._run_epoch_device(users[W * B:], items[W * B:])  # exactly K steps
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * K * B / (ms * 1e-3)
+
+    # ---- end to end through the public API (host ids) -------------------
+    e2e = None
+    if not a.no_e2e:
+        from spotlight_b200.interactions import Interactions
+        rs = np.random.RandomState(7 + rank)
+        hu = rs.randint(0, a.users, K * B).astype(np.int32)
+        hi = rs.randint(0, a.items, K * B).astype(np.int32)
+        inter = Interactions(hu, hi, num_users=a.users, num_items=a.items)
+        barrier()
+        t0 = time.perf_counter()
+        model.fit(inter)                                               # n_iter = 1 -> K steps
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * K * B / float(t.item()), 'unit': UNIT,
+               'h2d_bytes_per_step': 16 * B, 'd2h_bytes_per_step': 4,
+               'note': 'ImplicitFactorizationModel.fit(Interactions): numpy shuffle on one host '
+                       'thread (bit-exact RandomState stream), H2D of ids, device negatives, K '
+                       'fused steps, D2H of per-batch losses'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel durations and roofline ------------------------------
+    kb = kernel_breakdown(model, users, items, a, min(K, 50))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    R = 4 * a.dim
+    alg = {'mf_fwd': 3 * R + 60, 'mf_bwd': 7 * R + 84}        # bytes / interaction, DESIGN.md
+    dom = max(alg, key=lambda k: kb[k])
+    achieved = alg[dom] * B / (kb[dom] * 1e-3) / 1e9
+    step_ms = sum(kb.values())
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None,
+                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650',
+                'algorithmic_bytes_per_interaction': alg[dom],
+                'kernel_ms': kb,
+                'step_algorithmic': {'bytes_per_interaction': 6 * R + 40,
+                                     'achieved_gbs': (6 * R + 40) * B / (step_ms * 1e-3) / 1e9,
+                                     'frac': (6 * R + 40) * B / (step_ms * 1e-3) / 1e9 / peak}}
+
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        r = run_cpu_port(a, a.cpu_steps, 2)
+        cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+    n_chunks = (K + 63) // 64
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(a, world), 'epoch_loss': epoch_loss,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': K * 5 + n_chunks * 5,
+            'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        main_reference(args)
+    else:
+        main_ours(args)

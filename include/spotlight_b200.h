@@ -192,6 +192,12 @@ int64_t slb_mf_compact_rows(int64_t batch, int32_t n_neg, int32_t loss, int32_t 
 
 int slb_mf_train_step(const slb_mf_step_args* args, slb_stream_t stream);
 
+/* Profiling aid: launch only the kernels selected by `phases`
+ * (1 forward, 2 index scan, 4 index fill, 8 backward, 16 optimizer); calling
+ * it once per bit, in that order, equals slb_mf_train_step.  bench.py uses it
+ * to time each kernel with CUDA events. */
+int slb_mf_train_step_phases(const slb_mf_step_args* args, int32_t phases, slb_stream_t stream);
+
 /* M1  epoch pipeline: runs ceil(n / batch) consecutive training steps (last
  * one short, torch_utils.py:22-32) over device-resident shuffled ids with the
  * fused optimizer, without returning to the host between steps.

@@ -28,7 +28,7 @@ EXPORTS = (
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_compact_rows',
-    'slb_mf_train_step', 'slb_mf_fit_epoch',
+    'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
     'slb_seq_step_workspace_bytes', 'slb_seq_train_step', 'slb_seq_representation',
 )
@@ -100,6 +100,7 @@ def _declare(lib):
     lib.slb_mf_compact_rows.argtypes = [c_i64, c_i32, c_i32, c_i32]
     lib.slb_mf_compact_rows.restype = c_i64
     lib.slb_mf_train_step.argtypes = [P(MfStepArgs), c_vp]
+    lib.slb_mf_train_step_phases.argtypes = [P(MfStepArgs), c_i32, c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
     lib.slb_loss_workspace_bytes.argtypes = [c_i64]
     lib.slb_loss_workspace_bytes.restype = c_sz

@@ -402,7 +402,8 @@ int validate(const slb_mf_step_args* x) {
 }
 
 int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
-                const int64_t* negs, int64_t B, float* loss_out, cudaStream_t st) {
+                const int64_t* negs, int64_t B, float* loss_out, cudaStream_t st,
+                int phases = 0x1f) {
     // layout is sized for x->batch so that short last batches reuse the same carve
     MfLayout l = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
     MfDev a;
@@ -428,19 +429,27 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 8 ? want : static_cast<int64_t>(sms) * 8);
     if (grid < 1) grid = 1;
     if (grid > MF_MAX_GRID) grid = MF_MAX_GRID;
-    DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
-    SLB_LAUNCH_CHECK("mf_fwd_kernel");
-    seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
-    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    if (phases & 1) {
+        DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_fwd_kernel");
+    }
+    if (phases & 2) {
+        seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
+        SLB_LAUNCH_CHECK("seg_scan_kernel");
+    }
     int fgrid = static_cast<int>((2 * B + 255) / 256);
     if (fgrid > sms * 8) fgrid = sms * 8;
-    mf_fill_kernel<<<fgrid, 256, 0, st>>>(a);
-    SLB_LAUNCH_CHECK("mf_fill_kernel");
+    if (phases & 4) {
+        mf_fill_kernel<<<fgrid, 256, 0, st>>>(a);
+        SLB_LAUNCH_CHECK("mf_fill_kernel");
+    }
     int64_t bwant = (2 * B + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
-    DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
-    SLB_LAUNCH_CHECK("mf_bwd_kernel");
-    if (x->opt != SLB_OPT_NONE) {
+    if (phases & 8) {
+        DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_bwd_kernel");
+    }
+    if ((phases & 16) && x->opt != SLB_OPT_NONE) {
         DISPATCH_LPR(lpr, mf_apply_kernel, bgrid, MF_THREADS, st, a);
         SLB_LAUNCH_CHECK("mf_apply_kernel");
     }
@@ -467,6 +476,13 @@ int slb_mf_train_step(const slb_mf_step_args* x, slb_stream_t stream) {
     if (rc != SLB_OK) return rc;
     return launch_step(x, x->users, x->items, x->negs, x->batch, x->loss_out,
                        static_cast<cudaStream_t>(stream));
+}
+
+int slb_mf_train_step_phases(const slb_mf_step_args* x, int32_t phases, slb_stream_t stream) {
+    const int rc = validate(x);
+    if (rc != SLB_OK) return rc;
+    return launch_step(x, x->users, x->items, x->negs, x->batch, x->loss_out,
+                       static_cast<cudaStream_t>(stream), phases);
 }
 
 int slb_mf_fit_epoch(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,

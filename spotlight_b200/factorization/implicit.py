@@ -35,6 +35,17 @@ from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, poi
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffle
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """Per-device side stream for the sampler (module-level: models stay picklable)."""
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
            'route; construct the model with use_cuda=True.')
 
@@ -168,11 +179,11 @@ class ImplicitFactorizationModel(object):
             users, items = shuffle(user_ids, item_ids, random_state=self._random_state)
             user_ids_tensor = gpu(torch.from_numpy(users), self._use_cuda)
             item_ids_tensor = gpu(torch.from_numpy(items), self._use_cuda)
-            negatives = self._epoch_negatives(len(users))
 
             if route == 'epoch':
-                epoch_loss = self._fit_epoch_pipeline(user_ids_tensor, item_ids_tensor, negatives)
+                epoch_loss = self._run_epoch_device(user_ids_tensor, item_ids_tensor)
             else:
+                negatives = self._epoch_negatives(len(users))
                 epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
                                                       fused=(route == 'fused'))
 
@@ -182,8 +193,51 @@ class ImplicitFactorizationModel(object):
             if np.isnan(epoch_loss) or epoch_loss == 0.0:
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
 
-    def _fit_epoch_pipeline(self, users, items, negatives):
-        """One C call enqueues every minibatch step of the epoch."""
+    def _run_epoch_device(self, users, items, chunk_batches=64):
+        """The epoch pipeline over device-resident (already shuffled) ids.
+
+        Negatives are drawn chunk by chunk on a side stream (the MT19937 block
+        generator is a single-CTA kernel) while the main stream runs the
+        previous chunk's training steps; the per-batch losses are read back
+        once at the end.  Returns the epoch loss exactly as the reference
+        defines it: the mean of the per-minibatch losses (implicit.py:240,245).
+        """
+        n, B, n_neg = users.numel(), int(self._batch_size), self._n_neg()
+        dev = users.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        chunk = max(1, int(chunk_batches)) * B
+
+        def draw(count):
+            with torch.cuda.stream(side):
+                negs = sample_items(self._num_items, count * n_neg,
+                                    random_state=self._random_state, device=dev)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return negs, ev
+
+        keep, parts = [], []
+        lo = 0
+        nxt = draw(min(chunk, n))
+        while lo < n:
+            cnt = min(chunk, n - lo)
+            negs, ev = nxt
+            main.wait_event(ev)
+            parts.append(self._fit_epoch_pipeline(users[lo:lo + cnt], items[lo:lo + cnt], negs,
+                                                  sync=False))
+            keep.append(negs)
+            lo += cnt
+            if lo < n:
+                nxt = draw(min(chunk, n - lo))
+        host = torch.cat(parts).cpu().numpy().astype(np.float64)       # one sync per epoch
+        ws = ops.workspace('mf%d_%d' % (self._num_users, self._num_items), 0, dev)
+        if ops.workspace_error_flag(ws):
+            raise ValueError('ids out of range reached the device kernels')
+        return float(host.sum() / len(host))
+
+    def _fit_epoch_pipeline(self, users, items, negatives, sync=True):
+        """One C call enqueues every minibatch step of ``users``/``items``; returns the
+        device tensor of per-batch losses (``sync=False``) or their mean."""
         net, opt = self._net, self._optimizer
         lib = _lib.load()
         n, B, n_neg = users.numel(), int(self._batch_size), self._n_neg()
@@ -219,6 +273,8 @@ class ImplicitFactorizationModel(object):
             rc = lib.slb_mf_fit_epoch(ctypes.byref(a), ops._ptr(users), ops._ptr(items),
                                       ops._ptr(negatives), n, ops._ptr(losses), ops._stream())
             _lib.check(rc, 'mf_fit_epoch')
+            if not sync:
+                return losses
             # the reference averages float(loss.item()) per batch (implicit.py:240,245)
             host = losses.cpu().numpy().astype(np.float64)
             if ops.workspace_error_flag(ws):
