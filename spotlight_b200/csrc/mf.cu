@@ -168,6 +168,216 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Tile-structured forward (pointwise / bpr / hinge).
+//
+// A warp owns a tile of 32 consecutive interactions.  Lane l loads the three
+// ids and three biases of interaction l (coalesced 256-byte id loads, one DRAM
+// round trip per 32 interactions instead of per interaction), then the warp
+// walks the tile: each group of LPR lanes gathers the three rows of one
+// interaction with 128-bit loads and reduces the two dots with xor shuffles;
+// the results are handed back to the owning lane, which evaluates the loss,
+// emits the two gradient terms with coalesced 8-byte stores and issues the
+// integer row counts (32 lanes in parallel).
+// ---------------------------------------------------------------------------
+constexpr int MF_TILE_THREADS = 128;
+
+template <int LPR, int LOSS>
+__global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
+    __shared__ float sh_red[MF_TILE_THREADS / 32];
+    __shared__ bool is_last;
+    constexpr int GPW = 32 / LPR;            // groups per warp
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LPR - 1);
+    const int grp = lane / LPR;
+    const int D = a.D;
+    const float invB = 1.0f / static_cast<float>(a.B);
+    const int64_t ntiles = (a.B + 31) / 32;
+    const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
+    float lsum = 0.f;
+
+    for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (MF_TILE_THREADS / 32) + (threadIdx.x >> 5);
+         tile < ntiles; tile += wstride) {
+        const int64_t b = tile * 32 + lane;
+        const bool valid = b < a.B;
+        int64_t u64 = 0, i64 = 0, j64 = 0;
+        if (valid) { u64 = a.users[b]; i64 = a.items[b]; j64 = a.negs[b]; }
+        const bool bad = u64 < 0 || u64 >= a.U || i64 < 0 || i64 >= a.I || j64 < 0 || j64 >= a.I;
+        if (bad) { u64 = 0; i64 = 0; j64 = 0; }
+        const int u = static_cast<int>(u64), i = static_cast<int>(i64), j = static_cast<int>(j64);
+        const float ub = __ldg(a.bu + u), ib = __ldg(a.bi + i), jb = __ldg(a.bi + j);
+        float dpm = 0.f, dnm = 0.f;
+#pragma unroll 4
+        for (int s = 0; s < LPR; ++s) {
+            const int src = s * GPW + grp;
+            const int uu = __shfl_sync(0xffffffffu, u, src);
+            const int ii = __shfl_sync(0xffffffffu, i, src);
+            const int jj = __shfl_sync(0xffffffffu, j, src);
+            const float* ur = a.Wu + static_cast<int64_t>(uu) * D;
+            const float* qi = a.Wi + static_cast<int64_t>(ii) * D;
+            const float* qj = a.Wi + static_cast<int64_t>(jj) * D;
+            float dp = 0.f, dn = 0.f;
+            for (int c = gl * 4; c < D; c += LPR * 4) {
+                const float4 u4 = ldg4(ur + c), i4 = ldg4(qi + c), j4 = ldg4(qj + c);
+                dp += dot4(u4, i4);
+                dn += dot4(u4, j4);
+            }
+            dp = group_sum<LPR>(dp, 0xffffffffu);
+            dn = group_sum<LPR>(dn, 0xffffffffu);
+            const float tp = __shfl_sync(0xffffffffu, dp, (lane % GPW) * LPR);
+            const float tn = __shfl_sync(0xffffffffu, dn, (lane % GPW) * LPR);
+            if (lane / GPW == s) { dpm = tp; dnm = tn; }
+        }
+        if (valid) {
+            const float p = dpm + ub + ib, n = dnm + ub + jb;
+            float per, gp, gn;
+            pair_loss(LOSS, p, n, per, gp, gn);
+            lsum += per;
+            gp *= invB; gn *= invB;
+            if (bad) { atomicExch(a.err, 1); gp = 0.f; gn = 0.f; }
+            if (a.pos_out) a.pos_out[b] = p;
+            if (a.neg_out) a.neg_out[b] = n;
+            *reinterpret_cast<int2*>(a.t_a + 2 * b) = make_int2(u, u);
+            *reinterpret_cast<int2*>(a.t_b + 2 * b) = make_int2(i, j);
+            *reinterpret_cast<float2*>(a.t_g + 2 * b) = make_float2(gp, gn);
+            const int nu = (gp != 0.f) + (gn != 0.f);
+            if (nu) atomicAdd(a.seg.cnt + u, nu);
+            if (gp != 0.f) atomicAdd(a.seg.cnt + a.U + i, 1);
+            if (gn != 0.f) atomicAdd(a.seg.cnt + a.U + j, 1);
+        }
+    }
+    const float bsum = block_sum<MF_TILE_THREADS>(lsum, sh_red);
+    if (threadIdx.x == 0) {
+        a.partial[blockIdx.x] = bsum;
+        __threadfence();
+        is_last = atomicAdd(a.done, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        float v = 0.f;
+        for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += 32)
+            v += *reinterpret_cast<volatile float*>(a.partial + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) { *a.loss_out = v * invB; *a.done = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Tile-structured backward: a warp owns 32 consecutive segments (touched rows).
+// Lane l prefetches segment l's metadata and its first two terms (member ids,
+// g, partner row index) -- the dependent-load chain is paid once per 32 rows --
+// then lane groups accumulate g * partner_row for one segment each.  Segments
+// with more than two terms (4 % at B = 65536 on 100 K items) take the generic
+// sorted walk.
+// ---------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(MF_TILE_THREADS) mf_bwd_tile_kernel(MfDev a) {
+    constexpr int GPW = 32 / LPR;
+    constexpr int WARPS = MF_TILE_THREADS / 32;
+    constexpr int CAP = seg_sort_cap(LPR);
+    __shared__ int32_t sh_sort[WARPS * GPW * 2 * CAP];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LPR - 1);
+    const int grp = lane / LPR;
+    const unsigned gmask = group_mask(LPR);
+    int32_t* sh = sh_sort + ((threadIdx.x >> 5) * GPW + grp) * 2 * CAP;
+    const int D = a.D;
+    const int nseg = a.seg.totals[0];
+    const int nsegA = a.seg.totals[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
+        a.compact_counts[0] = nsegA;
+        a.compact_counts[1] = nseg - nsegA;
+    }
+    const int32_t* __restrict__ t_a = a.t_a;
+    const int32_t* __restrict__ t_b = a.t_b;
+    const float* __restrict__ t_g = a.t_g;
+    const int32_t* __restrict__ members = a.seg.members;
+    const int ntiles = (nseg + 31) / 32;
+    const int wstride = gridDim.x * WARPS;
+
+    for (int tile = blockIdx.x * WARPS + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+        const int sidx = tile * 32 + lane;
+        const bool valid = sidx < nseg;
+        int start = 0, len = 0, row = 0, p0 = 0, p1 = 0;
+        float g0 = 0.f, g1 = 0.f;
+        const bool isA = sidx < nsegA;
+        if (valid) {
+            start = a.seg.seg_start[sidx];
+            len = a.seg.seg_start[sidx + 1] - start;
+            row = a.seg.seg_row[sidx];
+            int m0 = members[start];
+            int m1 = len >= 2 ? members[start + 1] : m0;
+            if (m1 < m0) { const int tmp = m0; m0 = m1; m1 = tmp; }
+            const int32_t* pidx = isA ? t_b : t_a;
+            g0 = t_g[m0]; p0 = pidx[m0];
+            if (len >= 2) { g1 = t_g[m1]; p1 = pidx[m1]; }
+        }
+#pragma unroll 2
+        for (int it = 0; it < LPR; ++it) {
+            const int src = it * GPW + grp;
+            const int s_len = __shfl_sync(0xffffffffu, len, src);
+            const int s_row = __shfl_sync(0xffffffffu, row, src);
+            const int s_start = __shfl_sync(0xffffffffu, start, src);
+            const int s_p0 = __shfl_sync(0xffffffffu, p0, src);
+            const int s_p1 = __shfl_sync(0xffffffffu, p1, src);
+            const float s_g0 = __shfl_sync(0xffffffffu, g0, src);
+            const float s_g1 = __shfl_sync(0xffffffffu, g1, src);
+            const int s = tile * 32 + src;
+            if (s >= nseg) continue;                    // group-uniform
+            const bool sA = s < nsegA;
+            const float* ptab = sA ? a.Wi : a.Wu;
+            float* out;
+            if (a.grad_mode == SLB_GRAD_DENSE)
+                out = sA ? a.dWu + static_cast<int64_t>(s_row) * D : a.dWi + static_cast<int64_t>(s_row - a.U) * D;
+            else
+                out = sA ? a.gWu + static_cast<int64_t>(s) * D : a.gWi + static_cast<int64_t>(s - nsegA) * D;
+            float bacc;
+            if (s_len <= 2) {
+                const float* r0 = ptab + static_cast<int64_t>(s_p0) * D;
+                const float* r1 = ptab + static_cast<int64_t>(s_p1) * D;
+                for (int c = gl * 4; c < D; c += LPR * 4) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v0 = ldg4(r0 + c);
+                    if (s_len == 2) {
+                        const float4 v1 = ldg4(r1 + c);
+                        fma4(acc, s_g0, v0);
+                        fma4(acc, s_g1, v1);
+                    } else {
+                        fma4(acc, s_g0, v0);
+                    }
+                    st4(out + c, acc);
+                }
+                bacc = s_len == 2 ? (0.f + s_g0) + s_g1 : 0.f + s_g0;
+            } else {
+                const int32_t* pidx = sA ? t_b : t_a;
+                bacc = 0.f;
+                for (int c0 = 0; c0 < D; c0 += LPR * 4) {
+                    const int c = c0 + gl * 4;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float b2 = 0.f;
+                    seg_visit_sorted<LPR>(members, s_start, s_len, gl, gmask, sh, [&](int32_t t) {
+                        const float g = t_g[t];
+                        if (c < D) fma4(acc, g, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
+                        b2 += g;
+                    });
+                    if (c < D) st4(out + c, acc);
+                    bacc = b2;
+                }
+            }
+            if (gl == 0) {
+                if (a.grad_mode == SLB_GRAD_DENSE) {
+                    if (sA) a.dbu[s_row] = bacc; else a.dbi[s_row - a.U] = bacc;
+                } else {
+                    if (sA) { a.urows[s] = s_row; a.gbu[s] = bacc; }
+                    else { a.irows[s - nsegA] = s_row - a.U; a.gbi[s - nsegA] = bacc; }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) mf_fill_kernel(MfDev a) {
     seg_rearm(a.seg);
     const int64_t T = a.T;
@@ -369,6 +579,16 @@ int lpr_for_dim(int D) {
         default: KERNEL<32><<<grid, block, 0, stream>>>(__VA_ARGS__); break;                 \
     }
 
+#define DISPATCH_LPR2(lpr, KERNEL, P2, grid, block, stream, ...)                               \
+    switch (lpr) {                                                                           \
+        case 1: KERNEL<1, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;               \
+        case 2: KERNEL<2, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;               \
+        case 4: KERNEL<4, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;               \
+        case 8: KERNEL<8, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;               \
+        case 16: KERNEL<16, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;             \
+        default: KERNEL<32, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;             \
+    }
+
 int validate(const slb_mf_step_args* x) {
     SLB_REQUIRE(x != nullptr, "mf_train_step: null args");
     SLB_REQUIRE(x->batch > 0, "mf_train_step: batch must be > 0");
@@ -430,7 +650,17 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     if (grid < 1) grid = 1;
     if (grid > MF_MAX_GRID) grid = MF_MAX_GRID;
     if (phases & 1) {
-        DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
+        if (x->loss == SLB_LOSS_ADAPTIVE_HINGE) {
+            DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
+        } else {
+            int64_t tw = ((B + 31) / 32 + 3) / 4;
+            int tgrid = static_cast<int>(tw < MF_MAX_GRID ? tw : MF_MAX_GRID);
+            switch (x->loss) {
+                case SLB_LOSS_POINTWISE: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_POINTWISE, tgrid, MF_TILE_THREADS, st, a); break;
+                case SLB_LOSS_BPR: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_BPR, tgrid, MF_TILE_THREADS, st, a); break;
+                default: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_HINGE, tgrid, MF_TILE_THREADS, st, a); break;
+            }
+        }
         SLB_LAUNCH_CHECK("mf_fwd_kernel");
     }
     if (phases & 2) {
@@ -446,8 +676,10 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     int64_t bwant = (2 * B + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
     if (phases & 8) {
-        DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
-        SLB_LAUNCH_CHECK("mf_bwd_kernel");
+        int64_t tw = ((2 * B + 31) / 32 + 3) / 4;     // upper bound on segment tiles
+        int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+        DISPATCH_LPR(lpr, mf_bwd_tile_kernel, tgrid, MF_TILE_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     }
     if ((phases & 16) && x->opt != SLB_OPT_NONE) {
         DISPATCH_LPR(lpr, mf_apply_kernel, bgrid, MF_THREADS, st, a);
@@ -563,8 +795,11 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     const int groups = MF_THREADS / lpr;
     int64_t bwant = (n + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
-    DISPATCH_LPR(lpr, mf_bwd_kernel, bgrid, MF_THREADS, st, a);
-    SLB_LAUNCH_CHECK("mf_bwd_kernel");
+    (void)bgrid;
+    int64_t tw = ((n + 31) / 32 + 3) / 4;
+    int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+    DISPATCH_LPR(lpr, mf_bwd_tile_kernel, tgrid, MF_TILE_THREADS, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     return SLB_OK;
 }
 
