@@ -233,7 +233,7 @@ int slb_embedding_backward(const float* dout, const int64_t* ids, int64_t n, int
     const int g1 = grid_for((T + 255) / 256);
     emb_count_kernel<<<g1, 256, 0, st>>>(ids, T, hs, rows, l.keys, l.seg, l.flags + 4);
     SLB_LAUNCH_CHECK("emb_count_kernel");
-    seg_scan_kernel<<<static_cast<unsigned>(l.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(l.seg, rows);
+    seg_scan_launch(l.seg, rows, st);
     SLB_LAUNCH_CHECK("seg_scan_kernel");
     emb_fill_kernel<<<g1, 256, 0, st>>>(l.keys, T, l.seg);
     SLB_LAUNCH_CHECK("emb_fill_kernel");

@@ -182,24 +182,25 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
 // ---------------------------------------------------------------------------
 constexpr int MF_TILE_THREADS = 128;
 
-template <int LPR, int LOSS>
+template <int LPR, int LOSS, int TI>
 __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     __shared__ float sh_red[MF_TILE_THREADS / 32];
     __shared__ bool is_last;
     constexpr int GPW = 32 / LPR;            // groups per warp
+    constexpr int ITERS = TI / GPW > 0 ? TI / GPW : 1;
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
     const int D = a.D;
     const float invB = 1.0f / static_cast<float>(a.B);
-    const int64_t ntiles = (a.B + 31) / 32;
+    const int64_t ntiles = (a.B + TI - 1) / TI;
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
     float lsum = 0.f;
 
     for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (MF_TILE_THREADS / 32) + (threadIdx.x >> 5);
          tile < ntiles; tile += wstride) {
-        const int64_t b = tile * 32 + lane;
-        const bool valid = b < a.B;
+        const int64_t b = tile * TI + lane;
+        const bool valid = lane < TI && b < a.B;
         int64_t u64 = 0, i64 = 0, j64 = 0;
         if (valid) { u64 = a.users[b]; i64 = a.items[b]; j64 = a.negs[b]; }
         const bool bad = u64 < 0 || u64 >= a.U || i64 < 0 || i64 >= a.I || j64 < 0 || j64 >= a.I;
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
         const float ub = __ldg(a.bu + u), ib = __ldg(a.bi + i), jb = __ldg(a.bi + j);
         float dpm = 0.f, dnm = 0.f;
 #pragma unroll 4
-        for (int s = 0; s < LPR; ++s) {
-            const int src = s * GPW + grp;
+        for (int s = 0; s < ITERS; ++s) {
+            const int src = (s * GPW + grp) % TI;       // TI < GPW: surplus groups recompute
             const int uu = __shfl_sync(0xffffffffu, u, src);
             const int ii = __shfl_sync(0xffffffffu, i, src);
             const int jj = __shfl_sync(0xffffffffu, j, src);
@@ -266,112 +267,198 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
 
 // ---------------------------------------------------------------------------
 // Tile-structured backward: a warp owns 32 consecutive segments (touched rows).
-// Lane l prefetches segment l's metadata and its first two terms (member ids,
-// g, partner row index) -- the dependent-load chain is paid once per 32 rows --
-// then lane groups accumulate g * partner_row for one segment each.  Segments
-// with more than two terms (4 % at B = 65536 on 100 K items) take the generic
-// sorted walk.
+// Lane l prefetches segment l's metadata and its first four terms (member ids
+// sorted with a 5-comparator network, g, partner row index) -- the dependent
+// load chain is paid once per 32 rows -- then each lane group accumulates
+// g * partner_row for one segment per iteration with all row loads issued
+// before the first FMA.  Longer segments sort through shared memory and
+// prefetch their (g, partner) pairs lane-parallel before the row walk.
+//
+// MODE 0: every segment, gradients written (dense or compact).
+// MODE 1: item segments only, compact gradients (fused-optimizer path, runs
+//         first: it needs the *old* user rows).
+// MODE 2: user segments only; the row-wise optimizer is applied in place
+//         (partners are item rows, which MODE 1 no longer needs), so the user
+//         gradient is never written to memory.
 // ---------------------------------------------------------------------------
-template <int LPR>
-__global__ void __launch_bounds__(MF_TILE_THREADS) mf_bwd_tile_kernel(MfDev a) {
+__device__ __forceinline__ void cswap(int& x, int& y) {
+    const int lo = x < y ? x : y, hi = x < y ? y : x;
+    x = lo; y = hi;
+}
+
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a) {
     constexpr int GPW = 32 / LPR;
     constexpr int WARPS = MF_TILE_THREADS / 32;
     constexpr int CAP = seg_sort_cap(LPR);
-    __shared__ int32_t sh_sort[WARPS * GPW * 2 * CAP];
+    __shared__ int32_t sh_all[WARPS * GPW * 4 * CAP];
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
     const unsigned gmask = group_mask(LPR);
-    int32_t* sh = sh_sort + ((threadIdx.x >> 5) * GPW + grp) * 2 * CAP;
+    int32_t* sh = sh_all + ((threadIdx.x >> 5) * GPW + grp) * 4 * CAP;
     const int D = a.D;
     const int nseg = a.seg.totals[0];
     const int nsegA = a.seg.totals[2];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
+    if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
         a.compact_counts[0] = nsegA;
         a.compact_counts[1] = nseg - nsegA;
     }
+    const int seg_lo = MODE == 1 ? nsegA : 0;
+    const int seg_hi = MODE == 2 ? nsegA : nseg;
     const int32_t* __restrict__ t_a = a.t_a;
     const int32_t* __restrict__ t_b = a.t_b;
     const float* __restrict__ t_g = a.t_g;
     const int32_t* __restrict__ members = a.seg.members;
-    const int ntiles = (nseg + 31) / 32;
+    const int ntiles = (seg_hi - seg_lo + 31) / 32;
     const int wstride = gridDim.x * WARPS;
 
     for (int tile = blockIdx.x * WARPS + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
-        const int sidx = tile * 32 + lane;
-        const bool valid = sidx < nseg;
-        int start = 0, len = 0, row = 0, p0 = 0, p1 = 0;
-        float g0 = 0.f, g1 = 0.f;
-        const bool isA = sidx < nsegA;
+        const int sidx = seg_lo + tile * 32 + lane;
+        const bool valid = sidx < seg_hi;
+        int start = 0, len = 0, row = 0;
+        int p[4] = {0, 0, 0, 0};
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid) {
+            const bool isA = sidx < nsegA;
             start = a.seg.seg_start[sidx];
             len = a.seg.seg_start[sidx + 1] - start;
             row = a.seg.seg_row[sidx];
-            int m0 = members[start];
-            int m1 = len >= 2 ? members[start + 1] : m0;
-            if (m1 < m0) { const int tmp = m0; m0 = m1; m1 = tmp; }
-            const int32_t* pidx = isA ? t_b : t_a;
-            g0 = t_g[m0]; p0 = pidx[m0];
-            if (len >= 2) { g1 = t_g[m1]; p1 = pidx[m1]; }
+            if (len <= 4) {
+                int m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = k < len ? members[start + k] : 0x7fffffff;
+                cswap(m[0], m[1]); cswap(m[2], m[3]); cswap(m[0], m[2]); cswap(m[1], m[3]); cswap(m[1], m[2]);
+                const int32_t* pidx = isA ? t_b : t_a;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < len) { g[k] = t_g[m[k]]; p[k] = pidx[m[k]]; }
+            }
         }
-#pragma unroll 2
         for (int it = 0; it < LPR; ++it) {
             const int src = it * GPW + grp;
             const int s_len = __shfl_sync(0xffffffffu, len, src);
             const int s_row = __shfl_sync(0xffffffffu, row, src);
             const int s_start = __shfl_sync(0xffffffffu, start, src);
-            const int s_p0 = __shfl_sync(0xffffffffu, p0, src);
-            const int s_p1 = __shfl_sync(0xffffffffu, p1, src);
-            const float s_g0 = __shfl_sync(0xffffffffu, g0, src);
-            const float s_g1 = __shfl_sync(0xffffffffu, g1, src);
-            const int s = tile * 32 + src;
-            if (s >= nseg) continue;                    // group-uniform
+            int sp[4];
+            float sg[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                sp[k] = __shfl_sync(0xffffffffu, p[k], src);
+                sg[k] = __shfl_sync(0xffffffffu, g[k], src);
+            }
+            const int s = seg_lo + tile * 32 + src;
+            if (s >= seg_hi) continue;                    // group-uniform
             const bool sA = s < nsegA;
             const float* ptab = sA ? a.Wi : a.Wu;
-            float* out;
-            if (a.grad_mode == SLB_GRAD_DENSE)
-                out = sA ? a.dWu + static_cast<int64_t>(s_row) * D : a.dWi + static_cast<int64_t>(s_row - a.U) * D;
-            else
-                out = sA ? a.gWu + static_cast<int64_t>(s) * D : a.gWi + static_cast<int64_t>(s - nsegA) * D;
-            float bacc;
-            if (s_len <= 2) {
-                const float* r0 = ptab + static_cast<int64_t>(s_p0) * D;
-                const float* r1 = ptab + static_cast<int64_t>(s_p1) * D;
-                for (int c = gl * 4; c < D; c += LPR * 4) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 v0 = ldg4(r0 + c);
-                    if (s_len == 2) {
-                        const float4 v1 = ldg4(r1 + c);
-                        fma4(acc, s_g0, v0);
-                        fma4(acc, s_g1, v1);
-                    } else {
-                        fma4(acc, s_g0, v0);
+            const int64_t orow = sA ? s_row : s_row - a.U;
+            float* out = nullptr;
+            if (MODE != 2) {
+                if (a.grad_mode == SLB_GRAD_DENSE) out = (sA ? a.dWu : a.dWi) + orow * D;
+                else out = sA ? a.gWu + static_cast<int64_t>(s) * D : a.gWi + static_cast<int64_t>(s - nsegA) * D;
+            }
+            float* wrow = MODE == 2 ? a.Wu + orow * D : nullptr;
+            float* srow = (MODE == 2 && a.opt == SLB_OPT_ADAGRAD) ? a.sWu + orow * D : nullptr;
+            float bacc = 0.f;
+
+            int n_gen = 0;
+            if (s_len > 4 && s_len <= CAP) {
+                // sort member ids through shared memory, then prefetch (g, partner) lane-parallel
+                int32_t* in = sh;
+                int32_t* srt = sh + CAP;
+                float* pg = reinterpret_cast<float*>(sh + 2 * CAP);
+                int32_t* pp = sh + 3 * CAP;
+                for (int i = gl; i < s_len; i += LPR) in[i] = members[s_start + i];
+                __syncwarp(gmask);
+                for (int i = gl; i < s_len; i += LPR) {
+                    const int32_t m = in[i];
+                    int r = 0;
+                    for (int j = 0; j < s_len; ++j) r += in[j] < m;
+                    srt[r] = m;
+                }
+                __syncwarp(gmask);
+                const int32_t* pidx = sA ? t_b : t_a;
+                for (int i = gl; i < s_len; i += LPR) { pg[i] = t_g[srt[i]]; pp[i] = pidx[srt[i]]; }
+                __syncwarp(gmask);
+                n_gen = s_len;
+            }
+
+            for (int c = gl * 4; c < D; c += LPR * 4) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float b2 = 0.f;
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = w4;
+                if (MODE == 2) { w4 = ld4(wrow + c); if (srow) s4 = ld4(srow + c); }
+                if (s_len <= 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < s_len) v[k] = ldg4(ptab + static_cast<int64_t>(sp[k]) * D + c);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < s_len) { fma4(acc, sg[k], v[k]); b2 += sg[k]; }
+                } else if (n_gen) {
+                    const float* pg = reinterpret_cast<const float*>(sh + 2 * CAP);
+                    const int32_t* pp = sh + 3 * CAP;
+                    int i = 0;
+                    for (; i + 4 <= n_gen; i += 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] = ldg4(ptab + static_cast<int64_t>(pp[i + k]) * D + c);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { fma4(acc, pg[i + k], v[k]); b2 += pg[i + k]; }
                     }
+                    for (; i < n_gen; ++i) {
+                        fma4(acc, pg[i], ldg4(ptab + static_cast<int64_t>(pp[i]) * D + c));
+                        b2 += pg[i];
+                    }
+                } else {
+                    // hot row (> CAP terms): ordered selection walk, correct for any length
+                    const int32_t* pidx = sA ? t_b : t_a;
+                    seg_visit_sorted<LPR>(members, s_start, s_len, gl, gmask, sh, [&](int32_t t) {
+                        const float gg = t_g[t];
+                        fma4(acc, gg, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
+                        b2 += gg;
+                    });
+                }
+                bacc = b2;
+                if (MODE == 2) {
+                    float gv[4] = {acc.x + a.wd * w4.x, acc.y + a.wd * w4.y, acc.z + a.wd * w4.z, acc.w + a.wd * w4.w};
+                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    if (a.opt == SLB_OPT_SGD) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) wv[q] -= a.lr * gv[q];
+                    } else {
+                        float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            sv[q] += gv[q] * gv[q];
+                            wv[q] -= a.lr * gv[q] / (sqrtf(sv[q]) + a.eps);
+                        }
+                        st4(srow + c, make_float4(sv[0], sv[1], sv[2], sv[3]));
+                    }
+                    st4(wrow + c, make_float4(wv[0], wv[1], wv[2], wv[3]));
+                } else {
                     st4(out + c, acc);
                 }
-                bacc = s_len == 2 ? (0.f + s_g0) + s_g1 : 0.f + s_g0;
-            } else {
-                const int32_t* pidx = sA ? t_b : t_a;
-                bacc = 0.f;
-                for (int c0 = 0; c0 < D; c0 += LPR * 4) {
-                    const int c = c0 + gl * 4;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float b2 = 0.f;
-                    seg_visit_sorted<LPR>(members, s_start, s_len, gl, gmask, sh, [&](int32_t t) {
-                        const float g = t_g[t];
-                        if (c < D) fma4(acc, g, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
-                        b2 += g;
-                    });
-                    if (c < D) st4(out + c, acc);
-                    bacc = b2;
-                }
             }
+            if (n_gen) __syncwarp(gmask);        // scratch is reused by the next segment
             if (gl == 0) {
-                if (a.grad_mode == SLB_GRAD_DENSE) {
-                    if (sA) a.dbu[s_row] = bacc; else a.dbi[s_row - a.U] = bacc;
+                if (MODE == 2) {
+                    float* bw = a.bu + orow;
+                    const float gb = bacc + a.wd * *bw;
+                    if (a.opt == SLB_OPT_SGD) {
+                        *bw -= a.lr * gb;
+                    } else {
+                        float* bs = a.sbu + orow;
+                        const float sv = *bs + gb * gb;
+                        *bs = sv;
+                        *bw -= a.lr * gb / (sqrtf(sv) + a.eps);
+                    }
+                } else if (a.grad_mode == SLB_GRAD_DENSE) {
+                    if (sA) a.dbu[orow] = bacc; else a.dbi[orow] = bacc;
                 } else {
-                    if (sA) { a.urows[s] = s_row; a.gbu[s] = bacc; }
-                    else { a.irows[s - nsegA] = s_row - a.U; a.gbi[s - nsegA] = bacc; }
+                    if (sA) { a.urows[s] = orow; a.gbu[s] = bacc; }
+                    else { a.irows[s - nsegA] = orow; a.gbi[s - nsegA] = bacc; }
                 }
             }
         }
@@ -452,7 +539,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_bwd_kernel(MfDev a) {
 // SGD:     W -= lr * (g + wd*W)
 // Adagrad: g' = g + wd*W; state += g'^2; W -= lr * g' / (sqrt(state) + eps)
 //          (torch.optim.Adagrad with lr_decay = 0, initial_accumulator_value = 0)
-template <int LPR>
+template <int LPR, int ITEMS_ONLY>
 __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
     constexpr int GROUPS = MF_THREADS / LPR;
     const int gl = threadIdx.x & (LPR - 1);
@@ -460,7 +547,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
     const int D = a.D;
     const int nseg = a.seg.totals[0];
     const int nsegA = a.seg.totals[2];
-    for (int64_t s = static_cast<int64_t>(blockIdx.x) * GROUPS + gib; s < nseg;
+    for (int64_t s = (ITEMS_ONLY ? nsegA : 0) + static_cast<int64_t>(blockIdx.x) * GROUPS + gib; s < nseg;
          s += static_cast<int64_t>(gridDim.x) * GROUPS) {
         const bool isA = s < nsegA;
         const int64_t k = isA ? s : s - nsegA;
@@ -589,6 +676,16 @@ int lpr_for_dim(int D) {
         default: KERNEL<32, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;             \
     }
 
+#define DISPATCH_LPR3(lpr, KERNEL, P2, P3, grid, block, stream, ...)                           \
+    switch (lpr) {                                                                           \
+        case 1: KERNEL<1, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
+        case 2: KERNEL<2, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
+        case 4: KERNEL<4, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
+        case 8: KERNEL<8, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
+        case 16: KERNEL<16, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;         \
+        default: KERNEL<32, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;         \
+    }
+
 int validate(const slb_mf_step_args* x) {
     SLB_REQUIRE(x != nullptr, "mf_train_step: null args");
     SLB_REQUIRE(x->batch > 0, "mf_train_step: batch must be > 0");
@@ -653,18 +750,24 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
         if (x->loss == SLB_LOSS_ADAPTIVE_HINGE) {
             DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
         } else {
-            int64_t tw = ((B + 31) / 32 + 3) / 4;
+            // small batches: 8-interaction tiles so that every SM still gets ~36 warps
+            const bool small = B < static_cast<int64_t>(sms) * 36 * 32;
+            const int ti = small ? 8 : 32;
+            int64_t tw = ((B + ti - 1) / ti + 3) / 4;
             int tgrid = static_cast<int>(tw < MF_MAX_GRID ? tw : MF_MAX_GRID);
+#define FWD_TILE(L)                                                                             \
+    if (small) { DISPATCH_LPR3(lpr, mf_fwd_tile_kernel, L, 8, tgrid, MF_TILE_THREADS, st, a); } \
+    else { DISPATCH_LPR3(lpr, mf_fwd_tile_kernel, L, 32, tgrid, MF_TILE_THREADS, st, a); }
             switch (x->loss) {
-                case SLB_LOSS_POINTWISE: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_POINTWISE, tgrid, MF_TILE_THREADS, st, a); break;
-                case SLB_LOSS_BPR: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_BPR, tgrid, MF_TILE_THREADS, st, a); break;
-                default: DISPATCH_LPR2(lpr, mf_fwd_tile_kernel, SLB_LOSS_HINGE, tgrid, MF_TILE_THREADS, st, a); break;
+                case SLB_LOSS_POINTWISE: FWD_TILE(SLB_LOSS_POINTWISE); break;
+                case SLB_LOSS_BPR: FWD_TILE(SLB_LOSS_BPR); break;
+                default: FWD_TILE(SLB_LOSS_HINGE); break;
             }
         }
         SLB_LAUNCH_CHECK("mf_fwd_kernel");
     }
     if (phases & 2) {
-        seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
+        seg_scan_launch(a.seg, a.U, st);
         SLB_LAUNCH_CHECK("seg_scan_kernel");
     }
     int fgrid = static_cast<int>((2 * B + 255) / 256);
@@ -675,15 +778,26 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     }
     int64_t bwant = (2 * B + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
-    if (phases & 8) {
-        int64_t tw = ((2 * B + 31) / 32 + 3) / 4;     // upper bound on segment tiles
-        int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
-        DISPATCH_LPR(lpr, mf_bwd_tile_kernel, tgrid, MF_TILE_THREADS, st, a);
-        SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
-    }
-    if ((phases & 16) && x->opt != SLB_OPT_NONE) {
-        DISPATCH_LPR(lpr, mf_apply_kernel, bgrid, MF_THREADS, st, a);
-        SLB_LAUNCH_CHECK("mf_apply_kernel");
+    const int64_t tw = ((2 * B + 31) / 32 + 3) / 4;     // upper bound on segment tiles
+    const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+    if (x->opt == SLB_OPT_NONE) {
+        if (phases & 8) {
+            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 0, tgrid, MF_TILE_THREADS, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
+        }
+    } else {
+        // fused optimizer: item gradients first (they read the old user rows), then
+        // the user pass updates its rows in place, then the item rows are updated
+        if (phases & 8) {
+            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 1, tgrid, MF_TILE_THREADS, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<items>");
+            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 2, tgrid, MF_TILE_THREADS, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
+        }
+        if (phases & 16) {
+            DISPATCH_LPR2(lpr, mf_apply_kernel, 1, bgrid, MF_THREADS, st, a);
+            SLB_LAUNCH_CHECK("mf_apply_kernel<items>");
+        }
     }
     return SLB_OK;
 }
@@ -787,7 +901,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     if (g1 > sms * 8) g1 = sms * 8;
     mf_terms_kernel<<<g1, 256, 0, st>>>(a, gscores, user_broadcast);
     SLB_LAUNCH_CHECK("mf_terms_kernel");
-    seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.U);
+    seg_scan_launch(a.seg, a.U, st);
     SLB_LAUNCH_CHECK("seg_scan_kernel");
     mf_fill_kernel<<<g1, 256, 0, st>>>(a);
     SLB_LAUNCH_CHECK("mf_fill_kernel");
@@ -798,7 +912,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     (void)bgrid;
     int64_t tw = ((n + 31) / 32 + 3) / 4;
     int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
-    DISPATCH_LPR(lpr, mf_bwd_tile_kernel, tgrid, MF_TILE_THREADS, st, a);
+    DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 0, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     return SLB_OK;
 }

@@ -68,19 +68,47 @@ __device__ __forceinline__ uint32_t seg_sum(unsigned long long v) { return stati
 __device__ __forceinline__ uint32_t seg_nz(unsigned long long v) { return static_cast<uint32_t>((v >> 31) & 0x7fffffffull); }
 __device__ __forceinline__ unsigned long long seg_flag(unsigned long long v) { return v >> 62; }
 
-// Single-pass scan of cnt[0..Rpad): off = exclusive prefix sum; every non-zero
-// row gets a compact segment id (exclusive prefix of [cnt > 0]).
+// Scan of cnt[0..Rpad) in two launches with no inter-CTA waiting:
+//   seg_tilesum_kernel  per-tile (sum, non-zero count) -> status[tile]
+//   seg_scan_kernel     each tile sums the aggregates of all earlier tiles (a few
+//                       hundred L2-resident words), scans its own 4096 counters and
+//                       emits off[], the compact segment list and the totals.
 // RA: rows < RA belong to key space A; totals[2] = number of A segments.
 static __global__ void __launch_bounds__(SEG_SCAN_THREADS)
-seg_scan_kernel(SegIndex s, int64_t RA) {
-    __shared__ int32_t sh_tile;
-    __shared__ uint32_t sh_wsum[SEG_SCAN_THREADS / 32], sh_wnz[SEG_SCAN_THREADS / 32];
-    __shared__ uint32_t sh_prefix_sum, sh_prefix_nz;
-
-    if (threadIdx.x == 0) sh_tile = atomicAdd(s.ticket, 1);
+seg_tilesum_kernel(SegIndex s) {
+    __shared__ unsigned long long sh[SEG_SCAN_THREADS / 32];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SEG_SCAN_TILE + threadIdx.x * 4;
+    unsigned long long part = 0;      // [63:32] nz, [31:0] sum
+#pragma unroll
+    for (int i = 0; i < SEG_SCAN_ITEMS / 4; ++i) {
+        const int4 v = *reinterpret_cast<const int4*>(s.cnt + base + i * SEG_SCAN_THREADS * 4);
+        part += static_cast<unsigned long long>(static_cast<uint32_t>(v.x + v.y + v.z + v.w)) |
+                (static_cast<unsigned long long>((v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0)) << 32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
     __syncthreads();
-    const int tile = sh_tile;
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < SEG_SCAN_THREADS / 32; ++w) tot += sh[w];
+        s.status[blockIdx.x] = tot;
+    }
+}
+
+static __global__ void __launch_bounds__(SEG_SCAN_THREADS)
+seg_scan_kernel(SegIndex s, int64_t RA) {
+    __shared__ uint32_t sh_wsum[SEG_SCAN_THREADS / 32], sh_wnz[SEG_SCAN_THREADS / 32];
+    __shared__ unsigned long long sh_part[SEG_SCAN_THREADS / 32];
+    __shared__ uint32_t sh_prefix_sum, sh_prefix_nz;
+    const int tile = blockIdx.x;
     const int64_t base = static_cast<int64_t>(tile) * SEG_SCAN_TILE + threadIdx.x * SEG_SCAN_ITEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // prefix over earlier tiles (independent of this tile's own data: issue first)
+    unsigned long long part = 0;
+    for (int j = threadIdx.x; j < tile; j += SEG_SCAN_THREADS) part += s.status[j];
 
     int32_t c[SEG_SCAN_ITEMS];
 #pragma unroll
@@ -92,8 +120,6 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
 #pragma unroll
     for (int i = 0; i < SEG_SCAN_ITEMS; ++i) { tsum += c[i]; tnz += c[i] != 0; }
 
-    // warp inclusive scans
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t isum = tsum, inz = tnz;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -101,54 +127,25 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
         const uint32_t b = __shfl_up_sync(0xffffffffu, inz, o);
         if (lane >= o) { isum += a; inz += b; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 31) { sh_wsum[warp] = isum; sh_wnz[warp] = inz; }
+    if (lane == 0) sh_part[warp] = part;
     __syncthreads();
-    uint32_t wsum = 0, wnz = 0, bsum = 0, bnz = 0;
+    uint32_t wsum = 0, wnz = 0;
 #pragma unroll
-    for (int w = 0; w < SEG_SCAN_THREADS / 32; ++w) {
+    for (int w = 0; w < SEG_SCAN_THREADS / 32; ++w)
         if (w < warp) { wsum += sh_wsum[w]; wnz += sh_wnz[w]; }
-        bsum += sh_wsum[w]; bnz += sh_wnz[w];
-    }
-    const uint32_t esum = wsum + isum - tsum;   // exclusive within the tile
-    const uint32_t enz = wnz + inz - tnz;
-
-    // decoupled look-back by warp 0
-    if (warp == 0) {
-        volatile unsigned long long* st = s.status;
-        uint32_t psum = 0, pnz = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = seg_pack(SEG_FLAG_INC, bsum, bnz);
-        } else {
-            if (lane == 0) st[tile] = seg_pack(SEG_FLAG_AGG, bsum, bnz);
-            int j = tile - 1 - lane;
-            while (true) {
-                unsigned long long v = 0;
-                if (j >= 0) {
-                    do { v = st[j]; } while (seg_flag(v) == 0);
-                } else {
-                    v = seg_pack(SEG_FLAG_INC, 0, 0);
-                }
-                const unsigned inc = __ballot_sync(0xffffffffu, seg_flag(v) == SEG_FLAG_INC);
-                // lanes at or before the first INCLUSIVE predecessor contribute
-                const int first = inc ? __ffs(inc) - 1 : 32;
-                uint32_t cs = lane <= first ? seg_sum(v) : 0u;
-                uint32_t cz = lane <= first ? seg_nz(v) : 0u;
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    cs += __shfl_xor_sync(0xffffffffu, cs, o);
-                    cz += __shfl_xor_sync(0xffffffffu, cz, o);
-                }
-                psum += cs; pnz += cz;
-                if (inc) break;
-                j -= 32;
-            }
-            if (lane == 0) st[tile] = seg_pack(SEG_FLAG_INC, psum + bsum, pnz + bnz);
-        }
-        if (lane == 0) { sh_prefix_sum = psum; sh_prefix_nz = pnz; }
+        for (int w = 0; w < SEG_SCAN_THREADS / 32; ++w) tot += sh_part[w];
+        sh_prefix_sum = static_cast<uint32_t>(tot & 0xffffffffull);
+        sh_prefix_nz = static_cast<uint32_t>(tot >> 32);
     }
     __syncthreads();
-    uint32_t run = sh_prefix_sum + esum;
-    uint32_t seg = sh_prefix_nz + enz;
+    uint32_t run = sh_prefix_sum + wsum + isum - tsum;
+    uint32_t seg = sh_prefix_nz + wnz + inz - tnz;
 
 #pragma unroll
     for (int i = 0; i < SEG_SCAN_ITEMS; ++i) {
@@ -170,12 +167,17 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
     }
 }
 
+// Host helper: both launches of the scan.
+static inline void seg_scan_launch(const SegIndex& s, int64_t RA, cudaStream_t st) {
+    seg_tilesum_kernel<<<static_cast<unsigned>(s.ntiles), SEG_SCAN_THREADS, 0, st>>>(s);
+    seg_scan_kernel<<<static_cast<unsigned>(s.ntiles), SEG_SCAN_THREADS, 0, st>>>(s, RA);
+}
+
 // Re-arms the scan for the next use; run by any later kernel of the chain.
 __device__ __forceinline__ void seg_rearm(const SegIndex& s) {
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = tid; i < s.ntiles; i += nth) s.status[i] = 0ull;
-    if (tid == 0) *s.ticket = 0;
+    (void)tid; (void)nth;   // two-launch scan: nothing to re-arm (kept for call-site symmetry)
 }
 
 // members[off[key] + (--cnt[key])] = term.  Afterwards cnt is all-zero again.

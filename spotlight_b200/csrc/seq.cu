@@ -890,7 +890,7 @@ int slb_seq_train_step(const slb_seq_step_args* x, slb_stream_t stream) {
             if (i > 0) { dY = ping; float* tmp = ping; ping = pong; pong = tmp; }
         }
     }
-    seg_scan_kernel<<<static_cast<unsigned>(a.seg.ntiles), SEG_SCAN_THREADS, 0, st>>>(a.seg, a.seg.Rpad);
+    seg_scan_launch(a.seg, a.seg.Rpad, st);
     SLB_LAUNCH_CHECK("seg_scan_kernel");
     seq_fill_kernel<<<sq_grid((2 * B * S + 255) / 256), 256, 0, st>>>(a);
     SLB_LAUNCH_CHECK("seq_fill_kernel");

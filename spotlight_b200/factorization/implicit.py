@@ -218,9 +218,12 @@ class ImplicitFactorizationModel(object):
 
         keep, parts = [], []
         lo = 0
-        nxt = draw(min(chunk, n))
+        # chunks grow 1, 2, 4, ... batches up to `chunk_batches`: only the first
+        # (one-batch) draw is exposed, every later one hides behind training steps
+        cur = min(B, n)
+        nxt = draw(cur)
         while lo < n:
-            cnt = min(chunk, n - lo)
+            cnt = cur
             negs, ev = nxt
             main.wait_event(ev)
             parts.append(self._fit_epoch_pipeline(users[lo:lo + cnt], items[lo:lo + cnt], negs,
@@ -228,7 +231,8 @@ class ImplicitFactorizationModel(object):
             keep.append(negs)
             lo += cnt
             if lo < n:
-                nxt = draw(min(chunk, n - lo))
+                cur = min(min(2 * cnt, chunk), n - lo)
+                nxt = draw(cur)
         host = torch.cat(parts).cpu().numpy().astype(np.float64)       # one sync per epoch
         ws = ops.workspace('mf%d_%d' % (self._num_users, self._num_items), 0, dev)
         if ops.workspace_error_flag(ws):
