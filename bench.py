@@ -231,6 +231,72 @@ def kernel_breakdown(model, users, items, a, steps):
     return {nm: tot[nm] / steps for nm in names}
 
 
+def main_sharded(a, rank, world, local):
+    """N > 1: item rows range-sharded over the ranks, users owner-routed, NCCL
+    all-to-all of requests / rows / gradient rows (spotlight_b200/sharded.py).
+    Weak scaling: every rank processes `batch` interactions per step."""
+    import torch
+    import torch.distributed as dist
+    from spotlight_b200.sampling import sample_items
+    from spotlight_b200.sharded import GpuBackend, ShardedMF, ShardPlan, ShardState
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    B, K, W = a.batch, a.steps, a.warmup
+    plan = ShardPlan(a.users, a.items, world)
+    torch.manual_seed(100 + rank)
+    st = ShardState(plan, rank, a.dim, dev, lr=a.lr)
+    model = ShardedMF(plan, st, rank, GpuBackend(dev), cache_capacity=min(2 * B, a.items))
+    ulo, uhi = plan.user_range(rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n = (K + W) * B
+    users = torch.randint(ulo, uhi, (n,), device=dev, generator=g)
+    items = torch.randint(0, a.items, (n,), device=dev, generator=g)
+    negs = sample_items(a.items, n, random_state=np.random.RandomState(99 + rank), device=dev)
+
+    def run(lo, steps):
+        last = None
+        for k in range(steps):
+            s = slice((lo + k) * B, (lo + k + 1) * B)
+            last = model.step(users[s], items[s], negs[s], a.loss, world * B)
+        return last
+
+    run(0, W)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    model.stats = {'rows_requested': 0, 'bytes_a2a': 0}
+    e0.record()
+    last = run(W, K)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        cfg = workload_config(a, world)
+        cfg['parallelism'] = ('item rows range-sharded x%d, interactions routed to the user-owning '
+                              'rank, NCCL all-to-all of requests / rows / gradient rows' % world)
+        cfg['negatives'] = 'device MT19937 per rank (seeded per rank), pre-drawn'
+        a2a_gb = model.stats['bytes_a2a'] / 1e9
+        line = {'metric': METRIC, 'value': world * K * B / (ms * 1e-3), 'unit': UNIT,
+                'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': cfg, 'epoch_loss': float(last), 'clocks': clocks,
+                'e2e': None, 'gpu_launches': K * 30,
+                'nvlink': {'all_to_all_gbytes_per_rank': a2a_gb,
+                           'achieved_gbs_per_rank': a2a_gb / (ms * 1e-3),
+                           'rows_requested_per_step': model.stats['rows_requested'] / K},
+                'roofline': None, 'cpu_baseline': None}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def main_ours(a):
     import torch
     import torch.distributed as dist
@@ -238,7 +304,7 @@ def main_ours(a):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        return main_sharded(a, rank, world, local)
     model = build_model(a, local)
     dev = torch.device('cuda', local)
     B, K, W = a.batch, a.steps, a.warmup

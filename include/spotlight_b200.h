@@ -181,6 +181,15 @@ typedef struct slb_mf_step_args {
     float weight_decay;       /* added as wd*W[row] on touched rows */
     float eps;                /* adagrad */
     float* state_Wu; float* state_Wi; float* state_bu; float* state_bi; /* adagrad sums */
+    /* multi-GPU hooks (0 = single-GPU behaviour):
+     *  norm_batch   > 0: loss and gradients are normalised by this (global) batch
+     *                    size instead of `batch`; loss_out then holds this rank's
+     *                    share of the global mean.
+     *  opt_users_only != 0: with opt != NONE the optimizer is fused only into the
+     *                    user rows; item gradients are written per grad_mode and
+     *                    left to the caller (they belong to other ranks' shards). */
+    int64_t norm_batch;
+    int32_t opt_users_only;
     /* workspace */
     void* workspace; size_t workspace_bytes;
 } slb_mf_step_args;
@@ -205,6 +214,19 @@ int slb_mf_train_step_phases(const slb_mf_step_args* args, int32_t phases, slb_s
  * field; users/items/negs/batch/loss_out are overridden per step. */
 int slb_mf_fit_epoch(const slb_mf_step_args* step, const int64_t* users, const int64_t* items,
                      const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (e) multi-GPU routing: per-batch index bucketing for range-sharded item rows.
+ * Given n ids in [0, rows): uniq = the distinct ids ascending (so grouped by
+ * owner = id / chunk), inverse[t] = position of ids[t] in uniq, bounds[p] =
+ * first position in uniq owned by rank p (p = 0..nparts; bounds[nparts] = count).
+ * counts_out: device int64[nparts + 2] = bounds followed by the unique count.
+ * ---------------------------------------------------------------------- */
+size_t slb_unique_workspace_bytes(int64_t n, int64_t rows);
+int slb_unique_bucket(const int64_t* ids, int64_t n, int64_t rows, int64_t chunk, int32_t nparts,
+                      int64_t* uniq /* [min(n, rows)] */, int64_t* inverse /* [n] */,
+                      int64_t* counts_out, void* workspace, size_t workspace_bytes,
+                      slb_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * L1..L4 standalone losses -- replaces spotlight/losses.py:18-166 for the

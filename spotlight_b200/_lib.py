@@ -29,6 +29,7 @@ EXPORTS = (
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_compact_rows',
     'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch',
+    'slb_unique_workspace_bytes', 'slb_unique_bucket',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
     'slb_seq_step_workspace_bytes', 'slb_seq_train_step', 'slb_seq_representation',
 )
@@ -49,6 +50,7 @@ class MfStepArgs(ctypes.Structure):
         ('compact_counts', c_vp),
         ('opt', c_i32), ('lr', c_f32), ('weight_decay', c_f32), ('eps', c_f32),
         ('state_Wu', c_vp), ('state_Wi', c_vp), ('state_bu', c_vp), ('state_bi', c_vp),
+        ('norm_batch', c_i64), ('opt_users_only', c_i32),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
     ]
 
@@ -102,6 +104,9 @@ def _declare(lib):
     lib.slb_mf_train_step.argtypes = [P(MfStepArgs), c_vp]
     lib.slb_mf_train_step_phases.argtypes = [P(MfStepArgs), c_i32, c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
+    lib.slb_unique_workspace_bytes.argtypes = [c_i64, c_i64]
+    lib.slb_unique_workspace_bytes.restype = c_sz
+    lib.slb_unique_bucket.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
     lib.slb_loss_workspace_bytes.argtypes = [c_i64]
     lib.slb_loss_workspace_bytes.restype = c_sz
     lib.slb_pairwise_loss.argtypes = [c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,

@@ -27,6 +27,7 @@ constexpr int MF_THREADS = 256;
 
 struct MfDev {
     int64_t B;
+    int64_t NB;  // normalising batch (== B on one GPU, the global batch when sharded)
     int64_t T;   // number of rank-1 terms (2B for a training step)
     const int64_t* users; const int64_t* items; const int64_t* negs;
     int32_t loss; int32_t n_neg;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
     constexpr int GROUPS = MF_THREADS / LPR;
     const int64_t gid = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / LPR;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * GROUPS;
-    const float invB = 1.0f / static_cast<float>(a.B);
+    const float invB = 1.0f / static_cast<float>(a.NB);
     const int D = a.D;
     float lsum = 0.f;
 
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
     const int D = a.D;
-    const float invB = 1.0f / static_cast<float>(a.B);
+    const float invB = 1.0f / static_cast<float>(a.NB);
     const int64_t ntiles = (a.B + TI - 1) / TI;
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
     float lsum = 0.f;
@@ -700,16 +701,22 @@ int validate(const slb_mf_step_args* x) {
                 "mf_train_step: null pointer");
     SLB_REQUIRE(x->workspace != nullptr, "mf_train_step: null workspace");
     if (x->grad_mode == SLB_GRAD_DENSE) {
-        SLB_REQUIRE(x->dWu && x->dWi && x->dbu && x->dbi, "mf_train_step: dense mode needs dWu/dWi/dbu/dbi");
-        SLB_REQUIRE(x->opt == SLB_OPT_NONE, "mf_train_step: fused optimizer needs compact grads");
+        if (x->opt != SLB_OPT_NONE) {
+            SLB_REQUIRE(x->opt_users_only, "mf_train_step: a fully fused optimizer needs compact grads");
+            SLB_REQUIRE(x->dWi && x->dbi, "mf_train_step: users-only optimizer needs dWi/dbi for the item side");
+        } else {
+            SLB_REQUIRE(x->dWu && x->dWi && x->dbu && x->dbi, "mf_train_step: dense mode needs dWu/dWi/dbu/dbi");
+        }
     } else {
         SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT, "mf_train_step: bad grad_mode");
         SLB_REQUIRE(x->urows && x->gWu && x->gbu && x->irows && x->gWi && x->gbi && x->compact_counts,
                     "mf_train_step: compact mode needs urows/gWu/gbu/irows/gWi/gbi/compact_counts");
     }
     SLB_REQUIRE(x->opt >= SLB_OPT_NONE && x->opt <= SLB_OPT_ADAGRAD, "mf_train_step: bad optimizer");
-    if (x->opt == SLB_OPT_ADAGRAD)
-        SLB_REQUIRE(x->state_Wu && x->state_Wi && x->state_bu && x->state_bi, "mf_train_step: adagrad needs state");
+    if (x->opt == SLB_OPT_ADAGRAD) {
+        SLB_REQUIRE(x->state_Wu && x->state_bu, "mf_train_step: adagrad needs state");
+        SLB_REQUIRE(x->opt_users_only || (x->state_Wi && x->state_bi), "mf_train_step: adagrad needs item state");
+    }
     const size_t need = slb_mf_step_workspace_bytes(x->batch, x->n_neg, x->loss, x->num_users, x->num_items);
     if (x->workspace_bytes < need) {
         slb_set_error("mf_train_step: workspace too small (%zu < %zu)", x->workspace_bytes, need);
@@ -724,7 +731,7 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     // layout is sized for x->batch so that short last batches reuse the same carve
     MfLayout l = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
     MfDev a;
-    a.B = B; a.T = 2 * B; a.users = users; a.items = items; a.negs = negs;
+    a.B = B; a.NB = x->norm_batch > 0 ? x->norm_batch : B; a.T = 2 * B; a.users = users; a.items = items; a.negs = negs;
     a.loss = x->loss; a.n_neg = x->n_neg;
     a.U = x->num_users; a.I = x->num_items; a.D = x->dim;
     a.Wu = x->Wu; a.Wi = x->Wi; a.bu = x->bu; a.bi = x->bi;
@@ -794,7 +801,7 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
             DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 2, tgrid, MF_TILE_THREADS, st, a);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
         }
-        if (phases & 16) {
+        if ((phases & 16) && !x->opt_users_only) {
             DISPATCH_LPR2(lpr, mf_apply_kernel, 1, bgrid, MF_THREADS, st, a);
             SLB_LAUNCH_CHECK("mf_apply_kernel<items>");
         }
@@ -888,7 +895,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
         return SLB_ENOSPC;
     }
     MfDev a = {};
-    a.B = n; a.T = n; a.users = users; a.items = items;
+    a.B = n; a.NB = n; a.T = n; a.users = users; a.items = items;
     a.U = num_users; a.I = num_items; a.D = dim;
     a.Wu = const_cast<float*>(Wu); a.Wi = const_cast<float*>(Wi);
     a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;

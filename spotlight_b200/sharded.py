@@ -1,0 +1,215 @@
+"""Multi-GPU training step for the matrix-factorisation hot path.
+
+The reference has no distributed code at all; this is the new design the north
+star asks for.  One process per GPU (``torch.distributed``, NCCL over
+NVLink/NVSwitch):
+
+* **Partitioning.**  User rows (embedding, bias, optimizer state) are owned by
+  contiguous user-id ranges; every interaction of the global minibatch is
+  processed by the rank that owns its user, so user gathers and the in-place
+  user update are always local.  Item rows are sharded by contiguous index range
+  (``owner = id // ceil(num_items / world)``).
+* **Forward exchange.**  Each rank buckets the distinct item ids of its local
+  batch by owner (``unique_bucket``: one counting pass + scan, ids come out
+  ascending = grouped by owner), sends the request lists with an all-to-all,
+  owners gather rows + biases from their shard and a second all-to-all returns
+  them: each needed row crosses NVLink once per rank per step regardless of how
+  often the batch uses it.
+* **Local step.**  The fused kernels run on (local user shard, received row
+  cache) with the batch's item ids remapped onto the cache; loss and gradients
+  are normalised by the *global* batch size so the step equals the single-GPU
+  step of the concatenated batch.  User rows are updated in place.
+* **Backward exchange.**  The per-distinct-row item gradients (already reduced
+  locally, deterministically) travel back with the mirrored all-to-all; each
+  owner sums the contributions of its peers in rank order (segmented, no float
+  atomics) and applies the row-wise Adagrad update to its shard.
+* **Loss.**  One scalar all-reduce.
+
+All collectives are ``all_to_all_single`` / ``all_reduce`` of
+``torch.distributed``; the compute pieces are the product's CUDA kernels
+(:class:`GpuBackend`).  The routing logic is backend-agnostic so it can be
+exercised on CPU with ``gloo`` (tests/test_sharded_cpu.py injects a NumPy
+backend there; this module itself never imports the oracle).
+"""
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from spotlight_b200 import _lib, ops
+
+
+class ShardPlan(object):
+    """Contiguous range partition of users and items over ``world`` ranks."""
+
+    def __init__(self, num_users, num_items, world):
+        self.num_users, self.num_items, self.world = int(num_users), int(num_items), int(world)
+        self.uchunk = -(-self.num_users // self.world)
+        self.ichunk = -(-self.num_items // self.world)
+
+    def user_range(self, rank):
+        lo = min(rank * self.uchunk, self.num_users)
+        return lo, min(lo + self.uchunk, self.num_users)
+
+    def item_range(self, rank):
+        lo = min(rank * self.ichunk, self.num_items)
+        return lo, min(lo + self.ichunk, self.num_items)
+
+    def user_owner(self, user_ids):
+        return user_ids // self.uchunk
+
+
+class GpuBackend(object):
+    """The compute pieces of the sharded step on the product's CUDA kernels."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+
+    def unique_bucket(self, ids, rows, chunk, nparts):
+        """distinct ids ascending, inverse map, and per-owner boundaries (host list)."""
+        lib = _lib.load()
+        ids = ids.contiguous()
+        n = ids.numel()
+        uniq = torch.empty(min(n, rows), dtype=torch.int64, device=ids.device)
+        inverse = torch.empty(n, dtype=torch.int64, device=ids.device)
+        counts = torch.empty(nparts + 2, dtype=torch.int64, device=ids.device)
+        ws = ops.workspace('uq%d' % rows, lib.slb_unique_workspace_bytes(n, rows), ids.device)
+        rc = lib.slb_unique_bucket(ops._ptr(ids), n, rows, chunk, nparts, ops._ptr(uniq),
+                                   ops._ptr(inverse), ops._ptr(counts), ops._ptr(ws), ws.numel(),
+                                   ops._stream())
+        _lib.check(rc, 'unique_bucket')
+        host = counts.tolist()                       # the step's one bucketing sync
+        return uniq[:host[nparts + 1]], inverse, host[:nparts + 1]
+
+    def gather(self, W, b, local_ids):
+        rows = ops.embedding(W, local_ids, [], -1)
+        bias = ops.embedding(b.reshape(-1, 1), local_ids, [], -1).reshape(-1)
+        return rows, bias
+
+    def local_step(self, st, cache_rows, cache_bias, n_cache, users_local, pos_idx, neg_idx,
+                   loss, global_batch):
+        """Fused forward/backward on (user shard, row cache).  Updates the user
+        shard in place (row-wise Adagrad); returns (loss share, d cache rows, d cache bias)."""
+        lib = _lib.load()
+        cap, D = cache_rows.shape
+        a = ops.mf_step_args(st.Wu, cache_rows, st.bu, cache_bias, users_local, pos_idx, neg_idx,
+                             loss, 1)
+        loss_out = torch.empty(1, dtype=torch.float32, device=self.device)
+        dWi = torch.zeros((cap, D), dtype=torch.float32, device=self.device)
+        dbi = torch.zeros(cap, dtype=torch.float32, device=self.device)
+        a.loss_out = loss_out.data_ptr()
+        a.grad_mode = _lib.GRAD_DENSE
+        a.dWi, a.dbi = dWi.data_ptr(), dbi.data_ptr()
+        a.opt, a.lr, a.weight_decay, a.eps = _lib.OPT_ADAGRAD, st.lr, 0.0, st.eps
+        a.state_Wu, a.state_bu = st.sWu.data_ptr(), st.sbu.data_ptr()
+        a.norm_batch, a.opt_users_only = int(global_batch), 1
+        need = lib.slb_mf_step_workspace_bytes(a.batch, 1, a.loss, a.num_users, a.num_items)
+        ws = ops.workspace('mf%d_%d' % (a.num_users, a.num_items), need, self.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.slb_mf_train_step(ctypes.byref(a), ops._stream()), 'mf_train_step')
+        return loss_out.reshape(()), dWi[:n_cache], dbi[:n_cache]
+
+    def owner_update(self, st, local_ids, g_rows, g_bias):
+        """Sum the peers' gradient rows per shard row (rank order, deterministic)
+        and apply Adagrad to the item shard."""
+        rows = st.Wi.shape[0]
+        if local_ids.numel() == 0:
+            return
+        dW = ops.embedding_backward(g_rows.contiguous(), local_ids, [], rows, -1)
+        db = ops.embedding_backward(g_bias.reshape(-1, 1).contiguous(), local_ids, [], rows, -1)
+        adagrad_dense_(st.Wi, st.sWi, dW, st.lr, st.eps)
+        adagrad_dense_(st.bi, st.sbi, db.reshape(-1), st.lr, st.eps)
+
+
+def adagrad_dense_(W, state, grad, lr, eps):
+    """torch.optim.Adagrad update (lr_decay 0) on a small shard; rows with zero
+    gradient are unchanged, so this equals the row-wise update of touched rows."""
+    state.addcmul_(grad, grad)
+    W.addcdiv_(grad, state.sqrt().add_(eps), value=-lr)
+
+
+class ShardState(object):
+    """This rank's parameter shards and Adagrad state."""
+
+    def __init__(self, plan, rank, dim, device, lr=0.05, eps=1e-10, init=None):
+        ulo, uhi = plan.user_range(rank)
+        ilo, ihi = plan.item_range(rank)
+        self.ulo, self.uhi, self.ilo, self.ihi = ulo, uhi, ilo, ihi
+        self.lr, self.eps = float(lr), float(eps)
+        dev = torch.device(device)
+        if init is not None:            # slices of full tables (tests / checkpoints)
+            Wu, Wi, bu, bi = init
+            self.Wu = Wu[ulo:uhi].clone().to(dev)
+            self.Wi = Wi[ilo:ihi].clone().to(dev)
+            self.bu = bu[ulo:uhi].reshape(-1).clone().to(dev)
+            self.bi = bi[ilo:ihi].reshape(-1).clone().to(dev)
+        else:
+            self.Wu = torch.randn((uhi - ulo, dim), device=dev) / dim
+            self.Wi = torch.randn((ihi - ilo, dim), device=dev) / dim
+            self.bu = torch.zeros(uhi - ulo, device=dev)
+            self.bi = torch.zeros(ihi - ilo, device=dev)
+        self.sWu, self.sWi = torch.zeros_like(self.Wu), torch.zeros_like(self.Wi)
+        self.sbu, self.sbi = torch.zeros_like(self.bu), torch.zeros_like(self.bi)
+
+
+class ShardedMF(object):
+    """BPR/hinge/pointwise matrix factorisation with range-sharded rows."""
+
+    def __init__(self, plan, state, rank, backend, group=None, cache_capacity=None):
+        self.plan, self.st, self.rank, self.backend, self.group = plan, state, rank, backend, group
+        self.cache_capacity = cache_capacity
+        self.stats = {'rows_requested': 0, 'bytes_a2a': 0}
+
+    def _a2a(self, send, send_counts, recv_counts):
+        out = send.new_empty((sum(recv_counts),) + tuple(send.shape[1:]))
+        dist.all_to_all_single(out, send.contiguous(), output_split_sizes=list(recv_counts),
+                               input_split_sizes=list(send_counts), group=self.group)
+        self.stats['bytes_a2a'] += out.numel() * out.element_size()
+        return out
+
+    def step(self, users, items, negs, loss, global_batch):
+        """One training step on this rank's share of the global minibatch.
+
+        ``users`` must all be owned by this rank (global ids).  Returns the
+        *global* mean loss as a 0-dim tensor (identical on every rank).
+        """
+        plan, st, P = self.plan, self.st, self.plan.world
+        B = users.numel()
+        dev = users.device
+        # 1. bucket the distinct item ids by owner
+        ids = torch.cat([items, negs])
+        uniq, inverse, bounds = self.backend.unique_bucket(ids, plan.num_items, plan.ichunk, P)
+        send_counts = [bounds[p + 1] - bounds[p] for p in range(P)]
+        # 2. exchange the request sizes, then the requests
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        rc = torch.empty(P, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = rc.tolist()
+        req = self._a2a(uniq, send_counts, recv_counts)
+        # 3. owners gather rows/biases; rows travel back
+        local_req = req - st.ilo
+        rows, bias = self.backend.gather(st.Wi, st.bi, local_req)
+        n_cache = uniq.numel()
+        cap = self.cache_capacity or n_cache
+        cache_rows = self._a2a(rows, recv_counts, send_counts)
+        cache_bias = self._a2a(bias, recv_counts, send_counts)
+        if cap != n_cache:                 # fixed-capacity cache keeps the kernel workspace layout stable
+            full = cache_rows.new_zeros((cap, cache_rows.shape[1]))
+            full[:n_cache] = cache_rows
+            fb = cache_bias.new_zeros(cap)
+            fb[:n_cache] = cache_bias
+            cache_rows, cache_bias = full, fb
+        self.stats['rows_requested'] += n_cache
+        # 4. fused local step (user rows updated in place)
+        loss_share, g_rows, g_bias = self.backend.local_step(
+            st, cache_rows, cache_bias, n_cache, users - st.ulo, inverse[:B], inverse[B:], loss,
+            global_batch)
+        # 5. item gradients go home; owners reduce in rank order and update their shard
+        g_recv = self._a2a(g_rows, send_counts, recv_counts)
+        gb_recv = self._a2a(g_bias, send_counts, recv_counts)
+        self.backend.owner_update(st, local_req, g_recv, gb_recv)
+        # 6. global loss
+        total = loss_share.detach().clone().reshape(1)
+        dist.all_reduce(total, group=self.group)
+        return total.reshape(())

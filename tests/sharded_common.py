@@ -1,0 +1,100 @@
+"""Shared driver for the sharded-step tests (CPU/gloo with a NumPy backend,
+GPU/NCCL with the product backend): runs a few global steps on `world` ranks
+and on a single-process oracle, and returns both parameter sets."""
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from oracle import mf as omf
+
+
+class NumpyBackend(object):
+    """Oracle stand-in for spotlight_b200.sharded.GpuBackend (tests only)."""
+
+    def unique_bucket(self, ids, rows, chunk, nparts):
+        x = ids.numpy()
+        uniq, inverse = np.unique(x, return_inverse=True)
+        bounds = [int(np.searchsorted(uniq, p * chunk)) for p in range(nparts)] + [len(uniq)]
+        return torch.from_numpy(uniq), torch.from_numpy(inverse.astype(np.int64)), bounds
+
+    def gather(self, W, b, local_ids):
+        i = local_ids.numpy()
+        return torch.from_numpy(W.numpy()[i].copy()), torch.from_numpy(b.numpy()[i].copy())
+
+    def local_step(self, st, cache_rows, cache_bias, n_cache, users_local, pos_idx, neg_idx, loss,
+                   global_batch):
+        B = users_local.numel()
+        r = omf.mf_step(st.Wu.numpy().astype(np.float64), cache_rows.numpy().astype(np.float64),
+                        st.bu.numpy().astype(np.float64), cache_bias.numpy().astype(np.float64),
+                        users_local.numpy(), pos_idx.numpy(), neg_idx.numpy(), loss, 1, np.float64)
+        scale = B / float(global_batch)
+        for W, S, g in ((st.Wu, st.sWu, r['dWu'] * scale), (st.bu, st.sbu, r['dbu'].reshape(-1) * scale)):
+            s = S.numpy().astype(np.float64) + g * g
+            w = W.numpy().astype(np.float64) - st.lr * g / (np.sqrt(s) + st.eps)
+            S.copy_(torch.from_numpy(s.astype(np.float32)))
+            W.copy_(torch.from_numpy(w.astype(np.float32)))
+        return (torch.tensor(float(r['loss']) * scale, dtype=torch.float32),
+                torch.from_numpy((r['dWi'] * scale).astype(np.float32))[:n_cache],
+                torch.from_numpy((r['dbi'].reshape(-1) * scale).astype(np.float32))[:n_cache])
+
+    def owner_update(self, st, local_ids, g_rows, g_bias):
+        rows = st.Wi.shape[0]
+        dW = np.zeros((rows, st.Wi.shape[1]))
+        db = np.zeros(rows)
+        np.add.at(dW, local_ids.numpy(), g_rows.numpy().astype(np.float64))
+        np.add.at(db, local_ids.numpy(), g_bias.numpy().astype(np.float64))
+        for W, S, g in ((st.Wi, st.sWi, dW), (st.bi, st.sbi, db)):
+            s = S.numpy().astype(np.float64) + g * g
+            w = W.numpy().astype(np.float64) - st.lr * g / (np.sqrt(s) + st.eps)
+            S.copy_(torch.from_numpy(s.astype(np.float32)))
+            W.copy_(torch.from_numpy(w.astype(np.float32)))
+
+
+def make_problem(seed, U, I, D, B, steps):
+    rs = np.random.RandomState(seed)
+    Wu = (rs.randn(U, D) * 0.3).astype(np.float32)
+    Wi = (rs.randn(I, D) * 0.3).astype(np.float32)
+    bu = (rs.randn(U, 1) * 0.1).astype(np.float32)
+    bi = (rs.randn(I, 1) * 0.1).astype(np.float32)
+    batches = [(rs.randint(0, U, B).astype(np.int64), rs.randint(0, I, B).astype(np.int64),
+                rs.randint(0, I, B).astype(np.int64)) for _ in range(steps)]
+    return (Wu, Wi, bu, bi), batches
+
+
+def oracle_run(params, batches, loss, lr, eps=1e-10):
+    """Single-process reference: full-batch oracle step + dense Adagrad (float64)."""
+    P = [p.astype(np.float64) for p in params]
+    S = [np.zeros_like(p) for p in P]
+    losses = []
+    for users, items, negs in batches:
+        r = omf.mf_step(P[0], P[1], P[2], P[3], users, items, negs, loss, 1, np.float64)
+        losses.append(float(r['loss']))
+        for k, g in enumerate((r['dWu'], r['dWi'], r['dbu'], r['dbi'])):
+            S[k] += g * g
+            P[k] -= lr * g / (np.sqrt(S[k]) + eps)
+    return P, losses
+
+
+def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_capacity=None):
+    """Runs the steps on this rank; returns (all-gathered full tables, losses)."""
+    from spotlight_b200.sharded import ShardedMF, ShardPlan, ShardState
+    U, D = params[0].shape
+    I = params[1].shape[0]
+    plan = ShardPlan(U, I, world)
+    st = ShardState(plan, rank, D, device, lr=lr, init=[torch.from_numpy(p) for p in params])
+    model = ShardedMF(plan, st, rank, backend, cache_capacity=cache_capacity)
+    losses = []
+    for users, items, negs in batches:
+        mine = plan.user_owner(users) == rank
+        t = lambda x: torch.from_numpy(x[mine]).to(device)        # noqa: E731
+        losses.append(float(model.step(t(users), t(items), t(negs), loss, len(users))))
+    out = []
+    for shard, n, chunk in ((st.Wu, U, plan.uchunk), (st.Wi, I, plan.ichunk),
+                            (st.bu.reshape(-1, 1), U, plan.uchunk), (st.bi.reshape(-1, 1), I, plan.ichunk)):
+        pad = torch.zeros((chunk,) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        pad[:shard.shape[0]] = shard
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat(parts)[:n].cpu().numpy())
+    return out, losses, model.stats

@@ -1,0 +1,59 @@
+"""2-GPU NCCL test of the sharded step with the product kernels (run with
+``gpurun --gpus 2``; skipped on a single GPU)."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, assert_close
+
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+pytestmark = pytest.mark.gpu
+
+SHAPE = (7, 2000, 500, 32, 1024, 3)     # seed, U, I, D, B, steps
+
+
+def _worker(rank, world, port, loss, q):
+    import sharded_common as sc
+    from spotlight_b200.sharded import GpuBackend
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        params, batches = sc.make_problem(*SHAPE)
+        dev = torch.device('cuda', rank)
+        got, losses, stats = sc.sharded_run(rank, world, params, batches, loss, 0.05, dev,
+                                            GpuBackend(dev), cache_capacity=min(2 * SHAPE[4], SHAPE[2]))
+        if rank == 0:
+            q.put((got, losses, stats))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loss', ['bpr', 'pointwise'])
+def test_sharded_gpu_matches_oracle(loss):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import sharded_common as sc
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() * 3) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, loss, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses, stats = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params, batches = sc.make_problem(*SHAPE)
+    ref, ref_losses = sc.oracle_run(params, batches, loss, 0.05)
+    assert_close(np.array(losses), np.array(ref_losses), 1e-5, what='losses')
+    for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
+        assert_close(a, b, 1e-3, what=nm)       # Adagrad trajectory tolerance (see test_model_gpu)
