@@ -287,9 +287,10 @@ __device__ __forceinline__ void cswap(int& x, int& y) {
     x = lo; y = hi;
 }
 
-template <int LPR, int MODE>
+template <int LPR, int MODE, int TI>
 __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a) {
     constexpr int GPW = 32 / LPR;
+    constexpr int ITERS = TI / GPW > 0 ? TI / GPW : 1;
     constexpr int WARPS = MF_TILE_THREADS / 32;
     constexpr int CAP = seg_sort_cap(LPR);
     __shared__ int32_t sh_all[WARPS * GPW * 4 * CAP];
@@ -311,12 +312,12 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
     const int32_t* __restrict__ t_b = a.t_b;
     const float* __restrict__ t_g = a.t_g;
     const int32_t* __restrict__ members = a.seg.members;
-    const int ntiles = (seg_hi - seg_lo + 31) / 32;
+    const int ntiles = (seg_hi - seg_lo + TI - 1) / TI;
     const int wstride = gridDim.x * WARPS;
 
     for (int tile = blockIdx.x * WARPS + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
-        const int sidx = seg_lo + tile * 32 + lane;
-        const bool valid = sidx < seg_hi;
+        const int sidx = seg_lo + tile * TI + lane;
+        const bool valid = lane < TI && sidx < seg_hi;
         int start = 0, len = 0, row = 0;
         int p[4] = {0, 0, 0, 0};
         float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -336,20 +337,20 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
                     if (k < len) { g[k] = t_g[m[k]]; p[k] = pidx[m[k]]; }
             }
         }
-        for (int it = 0; it < LPR; ++it) {
-            const int src = it * GPW + grp;
-            const int s_len = __shfl_sync(0xffffffffu, len, src);
-            const int s_row = __shfl_sync(0xffffffffu, row, src);
-            const int s_start = __shfl_sync(0xffffffffu, start, src);
+        for (int it = 0; it < ITERS; ++it) {
+            const int src = it * GPW + grp;               // >= TI only when TI < GPW: idle group
+            const int s_len = __shfl_sync(0xffffffffu, len, src & 31);
+            const int s_row = __shfl_sync(0xffffffffu, row, src & 31);
+            const int s_start = __shfl_sync(0xffffffffu, start, src & 31);
             int sp[4];
             float sg[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                sp[k] = __shfl_sync(0xffffffffu, p[k], src);
-                sg[k] = __shfl_sync(0xffffffffu, g[k], src);
+                sp[k] = __shfl_sync(0xffffffffu, p[k], src & 31);
+                sg[k] = __shfl_sync(0xffffffffu, g[k], src & 31);
             }
-            const int s = seg_lo + tile * 32 + src;
-            if (s >= seg_hi) continue;                    // group-uniform
+            const int s = seg_lo + tile * TI + src;
+            if (src >= TI || s >= seg_hi) continue;       // group-uniform
             const bool sA = s < nsegA;
             const float* ptab = sA ? a.Wi : a.Wu;
             const int64_t orow = sA ? s_row : s_row - a.U;
@@ -785,20 +786,26 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     }
     int64_t bwant = (2 * B + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
-    const int64_t tw = ((2 * B + 31) / 32 + 3) / 4;     // upper bound on segment tiles
+    // small batches: 8-segment tiles so that every SM still gets enough warps
+    const bool bsmall = 2 * B < static_cast<int64_t>(sms) * 24 * 32;
+    const int bti = bsmall ? 8 : 32;
+    const int64_t tw = ((2 * B + bti - 1) / bti + 3) / 4;     // upper bound on segment tiles
     const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+#define BWD_TILE(MODE)                                                                              \
+    if (bsmall) { DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, MODE, 8, tgrid, MF_TILE_THREADS, st, a); } \
+    else { DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, MODE, 32, tgrid, MF_TILE_THREADS, st, a); }
     if (x->opt == SLB_OPT_NONE) {
         if (phases & 8) {
-            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 0, tgrid, MF_TILE_THREADS, st, a);
+            BWD_TILE(0);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
         }
     } else {
         // fused optimizer: item gradients first (they read the old user rows), then
         // the user pass updates its rows in place, then the item rows are updated
         if (phases & 8) {
-            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 1, tgrid, MF_TILE_THREADS, st, a);
+            BWD_TILE(1);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<items>");
-            DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 2, tgrid, MF_TILE_THREADS, st, a);
+            BWD_TILE(2);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
         }
         if ((phases & 16) && !x->opt_users_only) {
@@ -919,7 +926,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     (void)bgrid;
     int64_t tw = ((n + 31) / 32 + 3) / 4;
     int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
-    DISPATCH_LPR2(lpr, mf_bwd_tile_kernel, 0, tgrid, MF_TILE_THREADS, st, a);
+    DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     return SLB_OK;
 }

@@ -34,8 +34,13 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
+// Launched with ~200 KB of (unused) dynamic shared memory so the CTA owns its SM:
+// it runs on a side stream next to the training kernels, and sharing issue slots
+// with their CTAs slows this latency-bound loop by an order of magnitude.
 __global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* blocks, int64_t nblocks) {
+    extern __shared__ uint32_t sm_reserve[];
     __shared__ uint32_t buf[2][MT_N + 1];
+    if (nblocks < 0) sm_reserve[0] = 0;     // keep the reservation referenced
     const int t = threadIdx.x;
     for (int k = t; k < MT_N; k += 256) buf[0][k] = blocks[k];
     __syncthreads();
@@ -164,7 +169,17 @@ extern "C" {
 int slb_mt19937_fill(uint32_t* blocks, int64_t nblocks, slb_stream_t stream) {
     SLB_REQUIRE(blocks != nullptr && nblocks >= 1, "mt19937_fill: bad arguments");
     if (nblocks == 1) return SLB_OK;
-    mt19937_fill_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(blocks, nblocks);
+    constexpr int kReserve = 200 * 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mt19937_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kReserve) != cudaSuccess) {
+            slb_set_error("mt19937_fill: cannot reserve shared memory");
+            return SLB_ECUDA;
+        }
+        configured = true;
+    }
+    mt19937_fill_kernel<<<1, 256, kReserve, static_cast<cudaStream_t>(stream)>>>(blocks, nblocks);
     SLB_LAUNCH_CHECK("mt19937_fill_kernel");
     return SLB_OK;
 }

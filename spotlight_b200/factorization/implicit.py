@@ -42,7 +42,7 @@ def _side_stream(device):
     """Per-device side stream for the sampler (module-level: models stay picklable)."""
     key = torch.device(device).index
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
     return _SIDE_STREAMS[key]
 
 
@@ -208,10 +208,20 @@ class ImplicitFactorizationModel(object):
         side = _side_stream(dev)
         chunk = max(1, int(chunk_batches)) * B
 
+        # one buffer for the epoch's negatives (cached by the allocator across epochs);
+        # sampler scratch sized once for the largest chunk (no cudaMalloc mid-epoch)
+        negs_all = torch.empty(n * n_neg, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(side):
+            from spotlight_b200 import rng as _rng
+            _rng.reserve(self._num_items, min(chunk, n) * n_neg, dev)
+        drawn = [0]
+
         def draw(count):
+            lo_v = drawn[0]
+            drawn[0] += count * n_neg
             with torch.cuda.stream(side):
-                negs = sample_items(self._num_items, count * n_neg,
-                                    random_state=self._random_state, device=dev)
+                negs = sample_items(self._num_items, count * n_neg, random_state=self._random_state,
+                                    device=dev, out=negs_all[lo_v:drawn[0]])
                 ev = torch.cuda.Event()
                 ev.record(side)
             return negs, ev

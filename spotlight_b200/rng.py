@@ -32,15 +32,54 @@ def _mask_for(r):
     return m
 
 
-def sample_items_device(num_items, shape, random_state, device):
+_SCRATCH = {}
+
+
+def _scratch(dev, nwords, ws_bytes):
+    """Persistent (blocks, workspace, cursor) per device and stream: the sampler
+    runs every epoch, and a fresh cudaMalloc would synchronise the device."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
+    cur = _SCRATCH.get(key)
+    if cur is None or cur[0].numel() < nwords or cur[1].numel() < ws_bytes:
+        grow = 1.5 if cur is not None else 1.0
+        cur = (torch.empty(int(nwords * grow), dtype=torch.int32, device=dev),
+               torch.empty(int(ws_bytes * grow) + 4096, dtype=torch.uint8, device=dev),
+               torch.empty(2, dtype=torch.int64, device=dev),
+               torch.empty(_N, dtype=torch.int32).pin_memory(),
+               torch.empty(2, dtype=torch.int64).pin_memory())
+        _SCRATCH[key] = cur
+    return cur
+
+
+def reserve(num_items, count, device):
+    """Size the persistent sampler scratch for draws of up to ``count`` values."""
+    rng = int(num_items) - 1
+    if rng <= 0 or count <= 0:
+        return
+    lib = _lib.load()
+    p_accept = (rng + 1) / float(_mask_for(rng) + 1)
+    want = min(int(count), _MAX_CHUNK)
+    need_words = want / p_accept + 8.0 * math.sqrt(want * (1 - p_accept)) / p_accept + 64
+    nwords = (int(math.ceil((_N + need_words) / _N)) + 1) * _N
+    _scratch(torch.device(device), nwords, lib.slb_sample_workspace_bytes(nwords))
+
+
+def sample_items_device(num_items, shape, random_state, device, out=None):
     """``random_state.randint(0, num_items, shape, dtype=int64)`` as a CUDA tensor.
 
-    Advances ``random_state`` exactly as the NumPy call would.
+    Advances ``random_state`` exactly as the NumPy call would.  ``out``: optional
+    preallocated int64 CUDA tensor with ``prod(shape)`` elements.
     """
     shape = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
     count = int(np.prod(shape)) if len(shape) else 1
     dev = torch.device(device)
-    out = torch.empty(count, dtype=torch.int64, device=dev)
+    if out is None:
+        out = torch.empty(count, dtype=torch.int64, device=dev)
+    else:
+        out = out.reshape(-1)
+        if out.numel() != count or out.dtype != torch.int64 or not out.is_contiguous():
+            raise ValueError('sample_items_device: out must be a contiguous int64 tensor of %d' % count)
     rng = int(num_items) - 1
     if rng < 0:
         raise ValueError('num_items must be positive')
@@ -62,12 +101,13 @@ def sample_items_device(num_items, shape, random_state, device):
         # words needed ~ want / p  (+ 8 sigma), plus the unread tail of block 0
         need_words = want / p_accept + 8.0 * math.sqrt(want * (1 - p_accept)) / p_accept + 64
         nblocks = int(math.ceil((pos + need_words) / _N)) + 1
-        blocks = torch.empty(nblocks * _N, dtype=torch.int32, device=dev)
-        blocks[:_N].copy_(torch.from_numpy(key.view(np.int32)))
-        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
-        cursor = torch.tensor([pos, 0], dtype=torch.int64, device=dev)
         nwords = nblocks * _N
-        ws = torch.empty(lib.slb_sample_workspace_bytes(nwords), dtype=torch.uint8, device=dev)
+        blocks, ws, cursor, pin_key, pin_cur = _scratch(dev, nwords, lib.slb_sample_workspace_bytes(nwords))
+        pin_key.copy_(torch.from_numpy(key.view(np.int32)))
+        blocks[:_N].copy_(pin_key, non_blocking=True)
+        pin_cur[0], pin_cur[1] = pos, 0
+        cursor.copy_(pin_cur, non_blocking=True)
+        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
         chunk = out[done:done + want]
         rc = lib.slb_sample_bounded(_ptr(blocks), nwords, _ptr(cursor), ctypes.c_uint32(rng), want,
                                     _ptr(chunk), _ptr(ws), ws.numel(), _stream())

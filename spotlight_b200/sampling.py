@@ -10,7 +10,7 @@ to the NumPy call and ``random_state`` is advanced identically
 import numpy as np
 
 
-def sample_items(num_items, shape, random_state=None, device=None):
+def sample_items(num_items, shape, random_state=None, device=None, out=None):
     """Randomly sample item ids in ``[0, num_items)``.
 
     Returns a NumPy int64 array (``device is None``, host path identical to the
@@ -21,4 +21,4 @@ def sample_items(num_items, shape, random_state=None, device=None):
     if device is None:
         return random_state.randint(0, num_items, shape, dtype=np.int64)
     from spotlight_b200.rng import sample_items_device
-    return sample_items_device(num_items, shape, random_state, device)
+    return sample_items_device(num_items, shape, random_state, device, out=out)
