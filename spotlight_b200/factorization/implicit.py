@@ -46,6 +46,22 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
+def _to_device_ids(ids, device):
+    """Host id array -> int64 CUDA tensor (narrow on the wire, widened on the device)."""
+    arr = np.ascontiguousarray(ids)
+    if arr.dtype not in (np.int32, np.int64):
+        arr = arr.astype(np.int64)
+    return torch.from_numpy(arr).to(device).long()
+
+
+def _shuffled_order(n, random_state):
+    """The permutation ``shuffle`` applies: ``random_state.shuffle(arange(n))``
+    (torch_utils.py:46-47), advancing the MT19937 stream exactly as the reference."""
+    order = np.arange(n)
+    random_state.shuffle(order)
+    return order
+
+
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
            'route; construct the model with use_cuda=True.')
 
@@ -164,8 +180,8 @@ class ImplicitFactorizationModel(object):
     def fit(self, interactions, verbose=False):
         """Fit the model; repeated calls resume from the current weights and
         optimizer state (implicit.py:184-252)."""
-        user_ids = interactions.user_ids.astype(np.int64)
-        item_ids = interactions.item_ids.astype(np.int64)
+        user_ids = interactions.user_ids
+        item_ids = interactions.item_ids
 
         if not self._initialized:
             self._initialize(interactions)
@@ -174,16 +190,25 @@ class ImplicitFactorizationModel(object):
 
         self._check_input(user_ids, item_ids)
         route = self._route()
+        device = self._device()
+        # ids go to the device once per fit(); each epoch only the permutation travels
+        # (the reference re-uploads both shuffled id arrays, implicit.py:216-219)
+        users_dev = _to_device_ids(user_ids, device)
+        items_dev = _to_device_ids(item_ids, device)
 
         for epoch_num in range(self._n_iter):
-            users, items = shuffle(user_ids, item_ids, random_state=self._random_state)
-            user_ids_tensor = gpu(torch.from_numpy(users), self._use_cuda)
-            item_ids_tensor = gpu(torch.from_numpy(items), self._use_cuda)
+            # shuffle(): same stream consumption as random_state.shuffle(arange(n))
+            # (torch_utils.py:46-47); the fancy-index gathers run on the device
+            order = _shuffled_order(len(user_ids), self._random_state)
+            order_dev = torch.from_numpy(order).to(device)
+            user_ids_tensor = users_dev.index_select(0, order_dev)
+            item_ids_tensor = items_dev.index_select(0, order_dev)
+            del order_dev
 
             if route == 'epoch':
                 epoch_loss = self._run_epoch_device(user_ids_tensor, item_ids_tensor)
             else:
-                negatives = self._epoch_negatives(len(users))
+                negatives = self._epoch_negatives(len(user_ids))
                 epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
                                                       fused=(route == 'fused'))
 
