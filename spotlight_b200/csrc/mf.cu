@@ -282,13 +282,28 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
 //         (partners are item rows, which MODE 1 no longer needs), so the user
 //         gradient is never written to memory.
 // ---------------------------------------------------------------------------
+// Adagrad step  w -= lr * g / (sqrt(s) + eps)  with MUFU-based sqrt and division
+// (rsqrt 2 ulp, fast divide 2 ulp: ~5e-7 relative, far inside the 1e-5 parity
+// budget; the IEEE sqrtf + division pair costs ~20 instructions per element and
+// made the update kernel issue-bound).
+__device__ __forceinline__ float adagrad_delta(float lr, float g, float s, float eps) {
+    const float root = s > 0.f ? s * rsqrtf(s) : 0.f;
+    return __fdividef(lr * g, root + eps);
+}
+
 __device__ __forceinline__ void cswap(int& x, int& y) {
     const int lo = x < y ? x : y, hi = x < y ? y : x;
     x = lo; y = hi;
 }
 
+#ifndef BWD_MINB
+#define BWD_MINB 6
+#endif
+#ifndef BWD_FAST
+#define BWD_FAST 4
+#endif
 template <int LPR, int MODE, int TI>
-__global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a) {
+__global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(MfDev a) {
     constexpr int GPW = 32 / LPR;
     constexpr int ITERS = TI / GPW > 0 ? TI / GPW : 1;
     constexpr int WARPS = MF_TILE_THREADS / 32;
@@ -319,21 +334,22 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
         const int sidx = seg_lo + tile * TI + lane;
         const bool valid = lane < TI && sidx < seg_hi;
         int start = 0, len = 0, row = 0;
-        int p[4] = {0, 0, 0, 0};
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        int p[BWD_FAST] = {};
+        float g[BWD_FAST] = {};
         if (valid) {
             const bool isA = sidx < nsegA;
             start = a.seg.seg_start[sidx];
             len = a.seg.seg_start[sidx + 1] - start;
             row = a.seg.seg_row[sidx];
-            if (len <= 4) {
-                int m[4];
+            if (len <= BWD_FAST) {
+                int m[BWD_FAST];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) m[k] = k < len ? members[start + k] : 0x7fffffff;
-                cswap(m[0], m[1]); cswap(m[2], m[3]); cswap(m[0], m[2]); cswap(m[1], m[3]); cswap(m[1], m[2]);
+                for (int k = 0; k < BWD_FAST; ++k) m[k] = k < len ? members[start + k] : 0x7fffffff;
+                cswap(m[0], m[1]);
+                if (BWD_FAST == 4) { cswap(m[BWD_FAST - 2], m[BWD_FAST - 1]); cswap(m[0], m[BWD_FAST - 2]); cswap(m[1], m[BWD_FAST - 1]); cswap(m[1], m[BWD_FAST - 2]); }
                 const int32_t* pidx = isA ? t_b : t_a;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < BWD_FAST; ++k)
                     if (k < len) { g[k] = t_g[m[k]]; p[k] = pidx[m[k]]; }
             }
         }
@@ -342,10 +358,10 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
             const int s_len = __shfl_sync(0xffffffffu, len, src & 31);
             const int s_row = __shfl_sync(0xffffffffu, row, src & 31);
             const int s_start = __shfl_sync(0xffffffffu, start, src & 31);
-            int sp[4];
-            float sg[4];
+            int sp[BWD_FAST];
+            float sg[BWD_FAST];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < BWD_FAST; ++k) {
                 sp[k] = __shfl_sync(0xffffffffu, p[k], src & 31);
                 sg[k] = __shfl_sync(0xffffffffu, g[k], src & 31);
             }
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
             float bacc = 0.f;
 
             int n_gen = 0;
-            if (s_len > 4 && s_len <= CAP) {
+            if (s_len > BWD_FAST && s_len <= CAP) {
                 // sort member ids through shared memory, then prefetch (g, partner) lane-parallel
                 int32_t* in = sh;
                 int32_t* srt = sh + CAP;
@@ -390,13 +406,13 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
                 float b2 = 0.f;
                 float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = w4;
                 if (MODE == 2) { w4 = ld4(wrow + c); if (srow) s4 = ld4(srow + c); }
-                if (s_len <= 4) {
-                    float4 v[4];
+                if (s_len <= BWD_FAST) {
+                    float4 v[BWD_FAST];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < BWD_FAST; ++k)
                         if (k < s_len) v[k] = ldg4(ptab + static_cast<int64_t>(sp[k]) * D + c);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < BWD_FAST; ++k)
                         if (k < s_len) { fma4(acc, sg[k], v[k]); b2 += sg[k]; }
                 } else if (n_gen) {
                     const float* pg = reinterpret_cast<const float*>(sh + 2 * CAP);
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             sv[q] += gv[q] * gv[q];
-                            wv[q] -= a.lr * gv[q] / (sqrtf(sv[q]) + a.eps);
+                            wv[q] -= adagrad_delta(a.lr, gv[q], sv[q], a.eps);
                         }
                         st4(srow + c, make_float4(sv[0], sv[1], sv[2], sv[3]));
                     }
@@ -454,7 +470,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, 6) mf_bwd_tile_kernel(MfDev a
                         float* bs = a.sbu + orow;
                         const float sv = *bs + gb * gb;
                         *bs = sv;
-                        *bw -= a.lr * gb / (sqrtf(sv) + a.eps);
+                        *bw -= adagrad_delta(a.lr, gb, sv, a.eps);
                     }
                 } else if (a.grad_mode == SLB_GRAD_DENSE) {
                     if (sA) a.dbu[orow] = bacc; else a.dbi[orow] = bacc;
@@ -571,7 +587,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     sv[q] += gv[q] * gv[q];
-                    wv[q] -= a.lr * gv[q] / (sqrtf(sv[q]) + a.eps);
+                    wv[q] -= adagrad_delta(a.lr, gv[q], sv[q], a.eps);
                 }
                 st4(S + c, make_float4(sv[0], sv[1], sv[2], sv[3]));
             }
@@ -586,7 +602,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
                 float* bs = (isA ? a.sbu : a.sbi) + row;
                 const float sv = *bs + g * g;
                 *bs = sv;
-                *bw -= a.lr * g / (sqrtf(sv) + a.eps);
+                *bw -= adagrad_delta(a.lr, g, sv, a.eps);
             }
         }
     }
