@@ -183,3 +183,22 @@ def untemper(y):
     for _ in range(3):
         t = y ^ (t >> np.uint32(11))
     return t
+
+
+def jump(key, poly_words):
+    """State ``g(T) key`` for the jump polynomial ``g`` (624 uint32 words, bit i of
+    g = bit i%32 of word i//32), T = the one-word MT19937 transition.  Horner,
+    one coefficient bit per step; test arbiter for the device jump kernel and
+    for spotlight_b200/data/mt19937_jump.npy."""
+    ss = np.asarray(key, dtype=np.uint32)
+    acc = np.zeros(N, dtype=np.uint32)
+    o = 0
+    poly = int.from_bytes(np.asarray(poly_words, dtype='<u4').tobytes(), 'little')
+    for i in range(poly.bit_length() - 1, -1, -1):
+        a0, a1, am = int(acc[o]), int(acc[(o + 1) % N]), int(acc[(o + M) % N])
+        y = (a0 & 0x80000000) | (a1 & 0x7FFFFFFF)
+        acc[o] = am ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+        o = (o + 1) % N
+        if (poly >> i) & 1:
+            acc ^= np.roll(ss, o)
+    return np.roll(acc, -o)

@@ -63,6 +63,90 @@ __global__ void __launch_bounds__(256) mt19937_fill_kernel(uint32_t* blocks, int
     }
 }
 
+// Parallel variant: CTA r starts from states[r] (the generator state r*J blocks
+// after block 0, produced by the jump kernel; r = 0 is block 0 itself) and
+// writes blocks r*J + 1 .. r*J + J.  Only twisted blocks are written, so every
+// stored word is exact (a jumped state may carry garbage in the 31 low bits of
+// its word 0, which are not part of the MT19937 state).
+__global__ void __launch_bounds__(256)
+mt19937_fill_par_kernel(uint32_t* blocks, const uint32_t* __restrict__ states, int64_t J, int64_t nblocks) {
+    __shared__ uint32_t buf[2][MT_N + 1];
+    const int t = threadIdx.x;
+    const int64_t r = blockIdx.x;
+    const uint32_t* src = r == 0 ? blocks : states + r * MT_N;
+    for (int k = t; k < MT_N; k += 256) buf[0][k] = src[k];
+    __syncthreads();
+    int cur = 0;
+    for (int64_t j = 1; j <= J; ++j) {
+        const int64_t blk = r * J + j;
+        if (blk >= nblocks) break;
+        const uint32_t* o = buf[cur];
+        uint32_t* n = buf[cur ^ 1];
+        if (t < 227) n[t] = mt_mix(o[t], o[t + 1], o[t + MT_M]);
+        __syncthreads();
+        if (t < 227) n[227 + t] = mt_mix(o[227 + t], o[228 + t], n[t]);
+        __syncthreads();
+        if (t < 169) n[454 + t] = mt_mix(o[454 + t], o[455 + t], n[227 + t]);
+        if (t == 169) n[623] = mt_mix(o[623], n[0], n[396]);
+        __syncthreads();
+        uint32_t* dst = blocks + blk * MT_N;
+        for (int k = t; k < MT_N; k += 256) dst[k] = n[k];
+        cur ^= 1;
+    }
+}
+
+// Jump ahead: out = g(T) in, T = one-word MT19937 transition, g = x^(624 * 2^k) mod
+// the minimal polynomial (table from spotlight_b200/data/gen_mt19937_jump.py).
+// Horner over the 19968 coefficient bits, 32 bits per iteration: acc <- T^32(acc)
+// (32 new words are independent: recurrence distance 227), then
+// acc[t] ^= XOR_{m : bit m set} E[t + m] with E = the input state extended by 32
+// words, i.e. T^m(in)[t] = E[t + m].
+// Round `m` of the doubling schedule: CTA c jumps states[c << (m+1)] by 2^(k+m)
+// blocks into states[(c << (m+1)) + (1 << m)].
+constexpr int JUMP_THREADS = 640;
+
+__global__ void __launch_bounds__(JUMP_THREADS)
+mt19937_jump_kernel(uint32_t* states, const uint32_t* __restrict__ blocks0,
+                    const uint32_t* __restrict__ poly, int m, int P) {
+    __shared__ uint32_t E[MT_N + 32];
+    __shared__ uint32_t acc[MT_N];
+    const int t = threadIdx.x;
+    const int src_r = blockIdx.x << (m + 1);
+    const int dst_r = src_r + (1 << m);
+    if (dst_r >= P) return;
+    const uint32_t* in = src_r == 0 ? blocks0 : states + static_cast<int64_t>(src_r) * MT_N;
+    if (t < MT_N) { E[t] = in[t]; acc[t] = 0u; }
+    __syncthreads();
+    if (t < 32) E[MT_N + t] = mt_mix(E[t], E[t + 1], E[t + MT_M]);
+    __syncthreads();
+    int o = 0;                                  // circular base of acc
+    for (int w = MT_N - 1; w >= 0; --w) {
+        const uint32_t cw = __ldg(poly + w);
+        uint32_t nw = 0;
+        if (t < 32) {
+            int i0 = o + t; if (i0 >= MT_N) i0 -= MT_N;
+            int i1 = o + t + 1; if (i1 >= MT_N) i1 -= MT_N;
+            int im = o + t + MT_M; if (im >= MT_N) im -= MT_N;
+            nw = mt_mix(acc[i0], acc[i1], acc[im]);
+        }
+        __syncthreads();
+        if (t < 32) { int i0 = o + t; if (i0 >= MT_N) i0 -= MT_N; acc[i0] = nw; }
+        o += 32; if (o >= MT_N) o -= MT_N;
+        __syncthreads();
+        if (cw != 0u && t < MT_N) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+                if ((cw >> b) & 1u) v ^= E[t + b];
+            int i = o + t; if (i >= MT_N) i -= MT_N;
+            acc[i] ^= v;
+        }
+        __syncthreads();
+    }
+    uint32_t* out = states + static_cast<int64_t>(dst_r) * MT_N;
+    if (t < MT_N) { int i = o + t; if (i >= MT_N) i -= MT_N; out[t] = acc[i]; }
+}
+
 constexpr int SMP_THREADS = 256;
 constexpr int SMP_ITEMS = 8;
 constexpr int SMP_TILE = SMP_THREADS * SMP_ITEMS;
@@ -181,6 +265,35 @@ int slb_mt19937_fill(uint32_t* blocks, int64_t nblocks, slb_stream_t stream) {
     }
     mt19937_fill_kernel<<<1, 256, kReserve, static_cast<cudaStream_t>(stream)>>>(blocks, nblocks);
     SLB_LAUNCH_CHECK("mt19937_fill_kernel");
+    return SLB_OK;
+}
+
+int slb_mt19937_fill_parallel(uint32_t* blocks, int64_t nblocks, const uint32_t* jump_table,
+                              int32_t table_rows, uint32_t* states /* [128 * 624] */,
+                              slb_stream_t stream) {
+    SLB_REQUIRE(blocks && jump_table && states && nblocks >= 1, "mt19937_fill_parallel: bad arguments");
+    if (nblocks == 1) return SLB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // stride J = 2^k blocks per CTA, at most 128 CTAs
+    int k = 0;
+    while (((nblocks - 1 + (1ll << k) - 1) >> k) > 128) ++k;
+    const int64_t J = 1ll << k;
+    const int P = static_cast<int>((nblocks - 1 + J - 1) / J);
+    int top = 0;
+    while ((1 << (top + 1)) < P) ++top;               // highest m with 2^m < P
+    SLB_REQUIRE(k + top < table_rows, "mt19937_fill_parallel: jump table too small for %lld blocks",
+                static_cast<long long>(nblocks));
+    if (P > 1) {
+        for (int m = top; m >= 0; --m) {
+            const int grid = (P - (1 << m) + (1 << (m + 1)) - 1) >> (m + 1);
+            if (grid <= 0) continue;
+            mt19937_jump_kernel<<<grid, JUMP_THREADS, 0, st>>>(states, blocks,
+                                                               jump_table + static_cast<int64_t>(k + m) * MT_N, m, P);
+            SLB_LAUNCH_CHECK("mt19937_jump_kernel");
+        }
+    }
+    mt19937_fill_par_kernel<<<P, 256, 0, st>>>(blocks, states, J, nblocks);
+    SLB_LAUNCH_CHECK("mt19937_fill_par_kernel");
     return SLB_OK;
 }
 

@@ -33,6 +33,20 @@ def _mask_for(r):
 
 
 _SCRATCH = {}
+_JUMP = {}
+_PARALLEL_MIN_BLOCKS = 4096     # below this the single-CTA generator is as fast
+
+
+def _jump_table(dev):
+    """Device copy of the jump polynomials (data/mt19937_jump.npy) + state scratch."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _JUMP:
+        import os
+        tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data',
+                                   'mt19937_jump.npy'))
+        _JUMP[key] = (torch.from_numpy(tab.view(np.int32)).to(dev), int(tab.shape[0]),
+                      torch.empty(128 * _N, dtype=torch.int32, device=dev))
+    return _JUMP[key]
 
 
 def _scratch(dev, nwords, ws_bytes):
@@ -107,7 +121,12 @@ def sample_items_device(num_items, shape, random_state, device, out=None):
         blocks[:_N].copy_(pin_key, non_blocking=True)
         pin_cur[0], pin_cur[1] = pos, 0
         cursor.copy_(pin_cur, non_blocking=True)
-        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
+        if nblocks >= _PARALLEL_MIN_BLOCKS:
+            table, rows, states = _jump_table(dev)
+            _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
+                                                     _ptr(states), _stream()), 'mt19937_fill_parallel')
+        else:
+            _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
         chunk = out[done:done + want]
         rc = lib.slb_sample_bounded(_ptr(blocks), nwords, _ptr(cursor), ctypes.c_uint32(rng), want,
                                     _ptr(chunk), _ptr(ws), ws.numel(), _stream())

@@ -7,7 +7,7 @@ import pytest
 from conftest import assert_close, load_golden
 from oracle import mf as omf
 from oracle import seq as oseq
-from oracle.mt19937 import MT19937, temper, untemper
+from oracle.mt19937 import MT19937, jump, temper, twist, untemper
 from oracle.murmur import bloom_rows, murmurhash3_32
 
 MF_CASES = ['mf_pointwise', 'mf_bpr', 'mf_hinge', 'mf_adaptive_hinge', 'mf_bpr_d64']
@@ -45,6 +45,23 @@ def test_rng_golden_stream():
 def test_untemper_roundtrip():
     w = np.random.RandomState(1).randint(0, 2**32, 5000, dtype=np.uint64).astype(np.uint32)
     assert (untemper(temper(w)) == w).all()
+
+
+def test_jump_table_matches_sequential_twists():
+    """spotlight_b200/data/mt19937_jump.npy: row k jumps 2^k blocks (checked against
+    repeated twists for the reduced polynomials k = 5, 6, 9)."""
+    import os
+    from conftest import ROOT
+    tab = np.load(os.path.join(ROOT, 'spotlight_b200', 'data', 'mt19937_jump.npy'))
+    assert tab.shape == (27, 624)
+    key = np.random.RandomState(7).get_state()[1]
+    for k in (0, 5, 6, 9):
+        j = jump(key, tab[k])
+        ref = key.copy()
+        for _ in range(2 ** k):
+            ref = twist(ref)
+        # the 31 low bits of word 0 are not part of the MT19937 state
+        assert (j[1:] == ref[1:]).all() and ((int(j[0]) ^ int(ref[0])) & 0x80000000) == 0
 
 
 def test_murmur_matches_sklearn():
