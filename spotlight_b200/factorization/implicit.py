@@ -33,7 +33,7 @@ from spotlight_b200.factorization.representations import BilinearNet
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
 from spotlight_b200.sampling import sample_items
-from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffle
+from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
 
 _SIDE_STREAMS = {}
 
@@ -52,14 +52,6 @@ def _to_device_ids(ids, device):
     if arr.dtype not in (np.int32, np.int64):
         arr = arr.astype(np.int64)
     return torch.from_numpy(arr).to(device).long()
-
-
-def _shuffled_order(n, random_state):
-    """The permutation ``shuffle`` applies: ``random_state.shuffle(arange(n))``
-    (torch_utils.py:46-47), advancing the MT19937 stream exactly as the reference."""
-    order = np.arange(n)
-    random_state.shuffle(order)
-    return order
 
 
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
@@ -199,8 +191,8 @@ class ImplicitFactorizationModel(object):
         for epoch_num in range(self._n_iter):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
             # (torch_utils.py:46-47); the fancy-index gathers run on the device
-            order = _shuffled_order(len(user_ids), self._random_state)
-            order_dev = torch.from_numpy(order).to(device)
+            order = shuffled_order(len(user_ids), self._random_state)
+            order_dev = torch.from_numpy(order).to(device).long()
             user_ids_tensor = users_dev.index_select(0, order_dev)
             item_ids_tensor = items_dev.index_select(0, order_dev)
             del order_dev

@@ -22,7 +22,7 @@ from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, poi
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.sequence.representations import (PADDING_IDX, CNNNet, LSTMNet,
                                                      MixtureLSTMNet, PoolNet)
-from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffle
+from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
 
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
            'route; construct the model with use_cuda=True.')
@@ -123,7 +123,7 @@ class ImplicitSequenceModel(object):
         device = next(self._net.parameters()).device
 
         for epoch_num in range(self._n_iter):
-            sequences = shuffle(sequences, random_state=self._random_state)
+            sequences = sequences[shuffled_order(len(sequences), self._random_state)]
             sequences_tensor = gpu(torch.from_numpy(sequences), self._use_cuda)
             S = sequences_tensor.shape[1]
             # Per-minibatch draws of shape (n*B, S) (implicit.py:268-271, 283-285)

@@ -43,6 +43,28 @@ def shuffle(*arrays, **kwargs):
     return tuple(a[order] for a in arrays)
 
 
+def shuffled_order(n, random_state):
+    """The permutation ``random_state.shuffle(np.arange(n))`` produces, leaving
+    ``random_state`` in exactly the state NumPy would (torch_utils.py:46-47), computed
+    by the library's prefetching Fisher-Yates (csrc/host_shuffle.cpp, ~3x NumPy)."""
+    import ctypes
+    from spotlight_b200 import _lib
+    lib = _lib.load()
+    st = random_state.get_state()
+    if st[0] != 'MT19937' or n - 1 > 0xFFFFFFFE:
+        order = np.arange(n)
+        random_state.shuffle(order)
+        return order
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(st[2]))
+    order = np.empty(n, dtype=np.int32 if n < 2**31 else np.int64)
+    rc = lib.slb_host_shuffle_order(key.ctypes.data, ctypes.byref(pos), n, order.itemsize,
+                                    order.ctypes.data)
+    _lib.check(rc, 'host_shuffle_order')
+    random_state.set_state(('MT19937', key, pos.value, st[3], st[4]))
+    return order
+
+
 def assert_no_grad(variable):
     if variable.requires_grad:
         raise ValueError(

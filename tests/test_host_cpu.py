@@ -126,6 +126,22 @@ def test_shuffle_and_minibatch_follow_the_stream():
         shuffle(a, b[:5])
 
 
+def test_fast_host_shuffle_is_bit_exact():
+    """csrc/host_shuffle.cpp vs RandomState.shuffle: permutation and final state."""
+    from spotlight_b200.torch_utils import shuffled_order
+    for n in (0, 1, 2, 3, 100, 1000, 65537, 300_001):
+        a, b = np.random.RandomState(5), np.random.RandomState(5)
+        a.randint(0, 9, 11)
+        b.randint(0, 9, 11)
+        x = np.arange(n)
+        a.shuffle(x)
+        y = shuffled_order(n, b)
+        assert (x == y).all(), n
+        sa, sb = a.get_state(), b.get_state()
+        assert (sa[1] == sb[1]).all() and sa[2] == sb[2], n
+        assert (a.randint(0, 1000, 20) == b.randint(0, 1000, 20)).all()
+
+
 def test_sample_items_host_path_is_numpy():
     from spotlight_b200.sampling import sample_items
     r1, r2 = np.random.RandomState(9), np.random.RandomState(9)
