@@ -378,10 +378,11 @@ def main_ours(a):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {'value': world * K * B / float(t.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': 16 * B, 'd2h_bytes_per_step': 4,
-               'note': 'ImplicitFactorizationModel.fit(Interactions): numpy shuffle on one host '
-                       'thread (bit-exact RandomState stream), H2D of ids, device negatives, K '
-                       'fused steps, D2H of per-batch losses'}
+               'h2d_bytes_per_step': 12 * B, 'd2h_bytes_per_step': 4,
+               'note': 'ImplicitFactorizationModel.fit(Interactions) on host numpy ids: range check, '
+                       'H2D of ids, bit-exact Fisher-Yates permutation on one host thread '
+                       '(csrc/host_shuffle.cpp), H2D of the permutation, device gather, device '
+                       'negatives, K fused steps, D2H of per-batch losses'}
 
     if rank != 0:
         if world > 1:
