@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'a2a', 'dense'])
     return ap.parse_args()
 
 
@@ -275,7 +276,7 @@ def main_sharded(a, rank, world, local):
         last = None
         for k in range(steps):
             s = slice((lo + k) * B, (lo + k + 1) * B)
-            last = model.step(users[s], items[s], negs[s], a.loss, world * B)
+            last = model.step(users[s], items[s], negs[s], a.loss, world * B, a.exchange)
         return last
 
     run(0, W)
@@ -297,8 +298,11 @@ def main_sharded(a, rank, world, local):
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         cfg = workload_config(a, world)
-        cfg['parallelism'] = ('item rows range-sharded x%d, interactions routed to the user-owning '
-                              'rank, NCCL all-to-all of requests / rows / gradient rows' % world)
+        dense = a.exchange == 'dense' or (a.exchange == 'auto' and 2 * B >= a.items)
+        cfg['parallelism'] = ('item rows range-sharded x%d, interactions routed to the user-owning rank, '
+                              % world + ('whole-shard NCCL all-gather / reduce-scatter per step (2B >= '
+                                         'num_items: every row is needed by every rank)' if dense else
+                                         'NCCL all-to-all of requests / rows / gradient rows'))
         cfg['negatives'] = 'device MT19937 per rank (seeded per rank), pre-drawn'
         a2a_gb = model.stats['bytes_a2a'] / 1e9
         line = {'metric': METRIC, 'value': world * K * B / (ms * 1e-3), 'unit': UNIT,

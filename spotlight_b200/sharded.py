@@ -168,8 +168,64 @@ class ShardedMF(object):
         self.stats['bytes_a2a'] += out.numel() * out.element_size()
         return out
 
-    def step(self, users, items, negs, loss, global_batch):
+    def _dense_exchange_pays(self, local_batch):
+        """When a rank's 2*B item draws cover most of the table anyway, the
+        per-row routing (bucketing + 3 variable all-to-alls + two host syncs) moves
+        as many bytes as shipping whole shards; then all-gather / reduce-scatter of
+        the shards is the cheaper exchange."""
+        return 2 * local_batch >= self.plan.num_items
+
+    def step(self, users, items, negs, loss, global_batch, exchange='auto'):
         """One training step on this rank's share of the global minibatch.
+
+        ``exchange``: 'a2a' (per-row routing), 'dense' (whole-shard all-gather /
+        reduce-scatter) or 'auto'.
+        """
+        if exchange == 'dense' or (exchange == 'auto' and self._dense_exchange_pays(users.numel())):
+            return self.step_dense(users, items, negs, loss, global_batch)
+        return self.step_a2a(users, items, negs, loss, global_batch)
+
+    def step_dense(self, users, items, negs, loss, global_batch):
+        """Whole-shard exchange: all-gather the item shards, fused local step on the
+        full (transient) item table with raw ids, reduce-scatter the dense item
+        gradient back to its owners.  No bucketing, no host synchronisation."""
+        plan, st, P = self.plan, self.st, self.plan.world
+        chunk, D = plan.ichunk, st.Wi.shape[1]
+        dev = users.device
+        pad_W = st.Wi.new_zeros((chunk, D))
+        pad_W[:st.Wi.shape[0]] = st.Wi
+        pad_b = st.bi.new_zeros(chunk)
+        pad_b[:st.bi.shape[0]] = st.bi
+        full_W = st.Wi.new_empty((P * chunk, D))
+        full_b = st.bi.new_empty(P * chunk)
+        dist.all_gather_into_tensor(full_W, pad_W, group=self.group)
+        dist.all_gather_into_tensor(full_b, pad_b, group=self.group)
+        self.stats['bytes_a2a'] += (full_W.numel() + full_b.numel()) * 4
+        self.stats['rows_requested'] += P * chunk
+        loss_share, g_rows, g_bias = self.backend.local_step(
+            st, full_W, full_b, P * chunk, users - st.ulo, items, negs, loss, global_batch)
+        g_shard = self._reduce_scatter(g_rows.contiguous(), chunk)
+        gb_shard = self._reduce_scatter(g_bias.contiguous(), chunk)
+        self.stats['bytes_a2a'] += (g_rows.numel() + g_bias.numel()) * 4
+        n = st.Wi.shape[0]
+        adagrad_dense_(st.Wi, st.sWi, g_shard[:n], st.lr, st.eps)
+        adagrad_dense_(st.bi, st.sbi, gb_shard[:n], st.lr, st.eps)
+        total = loss_share.detach().clone().reshape(1)
+        dist.all_reduce(total, group=self.group)
+        return total.reshape(())
+
+    def _reduce_scatter(self, x, chunk):
+        out = x.new_empty((chunk,) + tuple(x.shape[1:]))
+        try:
+            dist.reduce_scatter_tensor(out, x, group=self.group)
+        except (RuntimeError, NotImplementedError):          # gloo: sum everywhere, keep our slice
+            y = x.clone()
+            dist.all_reduce(y, group=self.group)
+            out.copy_(y[self.rank * chunk:(self.rank + 1) * chunk])
+        return out
+
+    def step_a2a(self, users, items, negs, loss, global_batch):
+        """Per-row routing (the north-star exchange).
 
         ``users`` must all be owned by this rank (global ids).  Returns the
         *global* mean loss as a 0-dim tensor (identical on every rank).

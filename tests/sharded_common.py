@@ -76,7 +76,8 @@ def oracle_run(params, batches, loss, lr, eps=1e-10):
     return P, losses
 
 
-def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_capacity=None):
+def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_capacity=None,
+                exchange='a2a'):
     """Runs the steps on this rank; returns (all-gathered full tables, losses)."""
     from spotlight_b200.sharded import ShardedMF, ShardPlan, ShardState
     U, D = params[0].shape
@@ -88,7 +89,7 @@ def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_c
     for users, items, negs in batches:
         mine = plan.user_owner(users) == rank
         t = lambda x: torch.from_numpy(x[mine]).to(device)        # noqa: E731
-        losses.append(float(model.step(t(users), t(items), t(negs), loss, len(users))))
+        losses.append(float(model.step(t(users), t(items), t(negs), loss, len(users), exchange)))
     out = []
     for shard, n, chunk in ((st.Wu, U, plan.uchunk), (st.Wi, I, plan.ichunk),
                             (st.bu.reshape(-1, 1), U, plan.uchunk), (st.bi.reshape(-1, 1), I, plan.ichunk)):

@@ -23,7 +23,7 @@ from conftest import ROOT, assert_close
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def _worker(rank, world, port, loss, q):
+def _worker(rank, world, port, loss, q, exchange='a2a'):
     import sharded_common as sc
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -31,20 +31,22 @@ def _worker(rank, world, port, loss, q):
     try:
         params, batches = sc.make_problem(5, 101, 57, 8, 96, 3)
         got, losses, stats = sc.sharded_run(rank, world, params, batches, loss, 0.05, 'cpu',
-                                            sc.NumpyBackend())
+                                            sc.NumpyBackend(), exchange=exchange)
         if rank == 0:
             q.put((got, losses, stats))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,loss', [(2, 'bpr'), (3, 'bpr'), (2, 'pointwise')])
-def test_sharded_step_matches_single_process(world, loss):
+@pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (3, 'bpr', 'a2a'),
+                                                 (2, 'pointwise', 'a2a'), (2, 'bpr', 'dense'),
+                                                 (3, 'pointwise', 'dense')])
+def test_sharded_step_matches_single_process(world, loss, exchange):
     import sharded_common as sc
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 29500 + (os.getpid() + world * 7) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, loss, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, loss, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     got, losses, stats = q.get(timeout=240)
@@ -57,7 +59,8 @@ def test_sharded_step_matches_single_process(world, loss):
     for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
         assert_close(a, b, 2e-5, what=nm)
     # each distinct row crosses the wire once per rank per step, never per use
-    assert stats['rows_requested'] <= 3 * 57
+    if exchange == 'a2a':
+        assert stats['rows_requested'] <= 3 * 57
 
 
 def test_shard_plan_ranges():

