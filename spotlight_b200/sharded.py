@@ -88,13 +88,13 @@ class GpuBackend(object):
         return rows, bias
 
     def local_step(self, st, cache_rows, cache_bias, n_cache, users_local, pos_idx, neg_idx,
-                   loss, global_batch):
+                   loss, global_batch, n_neg=1):
         """Fused forward/backward on (user shard, row cache).  Updates the user
         shard in place (row-wise Adagrad); returns (loss share, d cache rows, d cache bias)."""
         lib = _lib.load()
         cap, D = cache_rows.shape
         a = ops.mf_step_args(st.Wu, cache_rows, st.bu, cache_bias, users_local, pos_idx, neg_idx,
-                             loss, 1)
+                             loss, n_neg)
         loss_out = torch.empty(1, dtype=torch.float32, device=self.device)
         dWi = torch.zeros((cap, D), dtype=torch.float32, device=self.device)
         dbi = torch.zeros(cap, dtype=torch.float32, device=self.device)
@@ -104,7 +104,7 @@ class GpuBackend(object):
         a.opt, a.lr, a.weight_decay, a.eps = _lib.OPT_ADAGRAD, st.lr, 0.0, st.eps
         a.state_Wu, a.state_bu = st.sWu.data_ptr(), st.sbu.data_ptr()
         a.norm_batch, a.opt_users_only = int(global_batch), 1
-        need = lib.slb_mf_step_workspace_bytes(a.batch, 1, a.loss, a.num_users, a.num_items)
+        need = lib.slb_mf_step_workspace_bytes(a.batch, n_neg, a.loss, a.num_users, a.num_items)
         ws = ops.workspace('mf%d_%d' % (a.num_users, a.num_items), need, self.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.slb_mf_train_step(ctypes.byref(a), ops._stream()), 'mf_train_step')
@@ -175,17 +175,25 @@ class ShardedMF(object):
         the shards is the cheaper exchange."""
         return 2 * local_batch >= self.plan.num_items
 
-    def step(self, users, items, negs, loss, global_batch, exchange='auto'):
+    def step(self, users, items, negs, loss, global_batch, exchange='auto', n_neg=1):
         """One training step on this rank's share of the global minibatch.
 
         ``exchange``: 'a2a' (per-row routing), 'dense' (whole-shard all-gather /
-        reduce-scatter) or 'auto'.
+        reduce-scatter) or 'auto'.  ``negs`` holds ``B * n_neg`` ids (adaptive hinge:
+        the flat ``randint`` block of the reference, implicit.py:266-275; its user
+        pairing ``users[f // n]`` is local because every user of this rank's batch
+        is owned by this rank).
         """
+        if loss == 'adaptive_hinge' or n_neg != 1:
+            # The reference pairs flat negative f = k*B + b with users[f // n] of the
+            # *global* batch (implicit.py:270-275), i.e. with user rows other ranks own;
+            # reproducing that needs a user-row exchange that is not built yet.
+            raise NotImplementedError('sharded adaptive hinge is not supported yet')
         if exchange == 'dense' or (exchange == 'auto' and self._dense_exchange_pays(users.numel())):
-            return self.step_dense(users, items, negs, loss, global_batch)
-        return self.step_a2a(users, items, negs, loss, global_batch)
+            return self.step_dense(users, items, negs, loss, global_batch, n_neg)
+        return self.step_a2a(users, items, negs, loss, global_batch, n_neg)
 
-    def step_dense(self, users, items, negs, loss, global_batch):
+    def step_dense(self, users, items, negs, loss, global_batch, n_neg=1):
         """Whole-shard exchange: all-gather the item shards, fused local step on the
         full (transient) item table with raw ids, reduce-scatter the dense item
         gradient back to its owners.  No bucketing, no host synchronisation."""
@@ -203,7 +211,7 @@ class ShardedMF(object):
         self.stats['bytes_a2a'] += (full_W.numel() + full_b.numel()) * 4
         self.stats['rows_requested'] += P * chunk
         loss_share, g_rows, g_bias = self.backend.local_step(
-            st, full_W, full_b, P * chunk, users - st.ulo, items, negs, loss, global_batch)
+            st, full_W, full_b, P * chunk, users - st.ulo, items, negs, loss, global_batch, n_neg)
         g_shard = self._reduce_scatter(g_rows.contiguous(), chunk)
         gb_shard = self._reduce_scatter(g_bias.contiguous(), chunk)
         self.stats['bytes_a2a'] += (g_rows.numel() + g_bias.numel()) * 4
@@ -224,7 +232,7 @@ class ShardedMF(object):
             out.copy_(y[self.rank * chunk:(self.rank + 1) * chunk])
         return out
 
-    def step_a2a(self, users, items, negs, loss, global_batch):
+    def step_a2a(self, users, items, negs, loss, global_batch, n_neg=1):
         """Per-row routing (the north-star exchange).
 
         ``users`` must all be owned by this rank (global ids).  Returns the
@@ -260,7 +268,7 @@ class ShardedMF(object):
         # 4. fused local step (user rows updated in place)
         loss_share, g_rows, g_bias = self.backend.local_step(
             st, cache_rows, cache_bias, n_cache, users - st.ulo, inverse[:B], inverse[B:], loss,
-            global_batch)
+            global_batch, n_neg)
         # 5. item gradients go home; owners reduce in rank order and update their shard
         g_recv = self._a2a(g_rows, send_counts, recv_counts)
         gb_recv = self._a2a(g_bias, send_counts, recv_counts)

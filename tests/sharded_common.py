@@ -23,11 +23,11 @@ class NumpyBackend(object):
         return torch.from_numpy(W.numpy()[i].copy()), torch.from_numpy(b.numpy()[i].copy())
 
     def local_step(self, st, cache_rows, cache_bias, n_cache, users_local, pos_idx, neg_idx, loss,
-                   global_batch):
+                   global_batch, n_neg=1):
         B = users_local.numel()
         r = omf.mf_step(st.Wu.numpy().astype(np.float64), cache_rows.numpy().astype(np.float64),
                         st.bu.numpy().astype(np.float64), cache_bias.numpy().astype(np.float64),
-                        users_local.numpy(), pos_idx.numpy(), neg_idx.numpy(), loss, 1, np.float64)
+                        users_local.numpy(), pos_idx.numpy(), neg_idx.numpy(), loss, n_neg, np.float64)
         scale = B / float(global_batch)
         for W, S, g in ((st.Wu, st.sWu, r['dWu'] * scale), (st.bu, st.sbu, r['dbu'].reshape(-1) * scale)):
             s = S.numpy().astype(np.float64) + g * g
@@ -51,24 +51,24 @@ class NumpyBackend(object):
             W.copy_(torch.from_numpy(w.astype(np.float32)))
 
 
-def make_problem(seed, U, I, D, B, steps):
+def make_problem(seed, U, I, D, B, steps, n_neg=1):
     rs = np.random.RandomState(seed)
     Wu = (rs.randn(U, D) * 0.3).astype(np.float32)
     Wi = (rs.randn(I, D) * 0.3).astype(np.float32)
     bu = (rs.randn(U, 1) * 0.1).astype(np.float32)
     bi = (rs.randn(I, 1) * 0.1).astype(np.float32)
     batches = [(rs.randint(0, U, B).astype(np.int64), rs.randint(0, I, B).astype(np.int64),
-                rs.randint(0, I, B).astype(np.int64)) for _ in range(steps)]
+                rs.randint(0, I, B * n_neg).astype(np.int64)) for _ in range(steps)]
     return (Wu, Wi, bu, bi), batches
 
 
-def oracle_run(params, batches, loss, lr, eps=1e-10):
+def oracle_run(params, batches, loss, lr, eps=1e-10, n_neg=1):
     """Single-process reference: full-batch oracle step + dense Adagrad (float64)."""
     P = [p.astype(np.float64) for p in params]
     S = [np.zeros_like(p) for p in P]
     losses = []
     for users, items, negs in batches:
-        r = omf.mf_step(P[0], P[1], P[2], P[3], users, items, negs, loss, 1, np.float64)
+        r = omf.mf_step(P[0], P[1], P[2], P[3], users, items, negs, loss, n_neg, np.float64)
         losses.append(float(r['loss']))
         for k, g in enumerate((r['dWu'], r['dWi'], r['dbu'], r['dbi'])):
             S[k] += g * g
