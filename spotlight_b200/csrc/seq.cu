@@ -14,9 +14,9 @@
 //   seq_mask_kernel      sum of the mask (seq != 0), id range check
 //   pool_rep_kernel      causal prefix mean; one CTA per sequence, 8 warps split
 //                        the time axis (two-level scan through shared memory)
-//   conv_gemm_kernel     causal dilated conv as a shifted-row GEMM (fp32 SIMT,
-//                        64x64x16 tiles): forward (+bias, act, residual) and
-//                        input-gradient modes
+//   conv_gemm_kernel     causal dilated conv as a shifted-row GEMM on the tensor cores
+//                        (mma.sync TF32, 3xTF32 split for fp32-level accuracy, 64x64x16
+//                        tiles): forward (+bias, act, residual) and input-gradient modes
 //   conv_dw_kernel       weight gradient, split over positions + fixed-order reduce
 //   seq_score_kernel     one lane group per position: dots, loss, d loss/d r,
 //                        target-role contribution rows, row counts
@@ -417,11 +417,58 @@ struct ConvGemm {
     int accumulate;
 };
 
+// Tensor-core inner product with fp32-level accuracy: mma.sync m16n8k8 TF32 with the
+// 3xTF32 error-compensated split (a = a_hi + a_lo, b = b_hi + b_lo; the product keeps
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), accumulating in fp32.  Relative error ~2^-21,
+// inside the 1e-5 parity budget that plain TF32 (2^-11) would miss (SURVEY hard part 4).
+// Tiles live in shared memory as As[k][row] / Bs[k][col] with a 72-float stride so the
+// fragment loads (k = lane%4, row/col = lane/4) are bank-conflict free.
+constexpr int TS = 72;      // padded tile stride
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// One GK = 16 deep chunk for a warp's 16 x 32 output tile (4 n-subtiles of 8).
+__device__ __forceinline__ void warp_mma_chunk(const float (*As)[TS], const float (*Bs)[TS], int wm, int wn,
+                                               int lane, float (&acc)[4][4]) {
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int k8 = 0; k8 < GK; k8 += 8) {
+        uint32_t ah[4], al[4];
+        split_tf32(As[k8 + tq][wm * 16 + gq], ah[0], al[0]);
+        split_tf32(As[k8 + tq][wm * 16 + gq + 8], ah[1], al[1]);
+        split_tf32(As[k8 + tq + 4][wm * 16 + gq], ah[2], al[2]);
+        split_tf32(As[k8 + tq + 4][wm * 16 + gq + 8], ah[3], al[3]);
+#pragma unroll
+        for (int ns = 0; ns < 4; ++ns) {
+            uint32_t bh[2], bl[2];
+            split_tf32(Bs[k8 + tq][wn * 32 + ns * 8 + gq], bh[0], bl[0]);
+            split_tf32(Bs[k8 + tq + 4][wn * 32 + ns * 8 + gq], bh[1], bl[1]);
+            mma_tf32(acc[ns], al, bh);
+            mma_tf32(acc[ns], ah, bl);
+            mma_tf32(acc[ns], ah, bh);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvGemm g) {
-    __shared__ float As[GK][GM + 4];
-    __shared__ float Bs[GK][GN];
+    __shared__ float As[GK][TS];
+    __shared__ float Bs[GK][TS];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
     const int64_t M = g.B * g.Tout;
     const int64_t m0 = static_cast<int64_t>(blockIdx.x) * GM;
     const int n0 = blockIdx.y * GN;
@@ -448,44 +495,40 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(ConvGemm g) {
             As[ac][ar] = av.x; As[ac + 1][ar] = av.y; As[ac + 2][ar] = av.z; As[ac + 3][ar] = av.w;
             *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
             __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < GK; ++kk) {
-                const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-                const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-                const float a_[4] = {a4.x, a4.y, a4.z, a4.w};
-                const float b_[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a_[x], b_[y], acc[x][y]);
-            }
+            warp_mma_chunk(As, Bs, wm, wn, lane, acc);
         }
     }
-    const int n = n0 + tx * 4;
-    if (n >= D) return;
+    // epilogue: thread owns rows (wm*16 + gq, +8), column pairs (wn*32 + ns*8 + 2*tq, +1)
+    const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const int64_t m = m0 + ty * 4 + x;
+    for (int half = 0; half < 2; ++half) {
+        const int64_t m = m0 + wm * 16 + gq + half * 8;
         if (m >= M) continue;
         const int64_t b = m / g.Tout;
         const int t = static_cast<int>(m - b * g.Tout);
-        float v[4] = {acc[x][0], acc[x][1], acc[x][2], acc[x][3]};
-        float4 res = make_float4(0, 0, 0, 0);
         const int rt = t + g.res_shift;
-        if (g.Res && rt >= 0 && rt < g.res_T) res = ld4(g.Res + (b * g.res_T + rt) * D + n);
-        if (g.mode == 0) {
-            const float4 bb = ldg4(g.bias + n);
-            v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+        const bool resok = g.Res && rt >= 0 && rt < g.res_T;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) v[y] = g.nonlin == 0 ? tanhf(v[y]) : fmaxf(v[y], 0.f);
-            st4(g.Aout + m * D + n, make_float4(v[0], v[1], v[2], v[3]));
+        for (int ns = 0; ns < 4; ++ns) {
+            const int n = n0 + wn * 32 + ns * 8 + 2 * tq;
+            if (n >= D) continue;
+            float v0 = acc[ns][half * 2], v1 = acc[ns][half * 2 + 1];
+            float2 res = make_float2(0.f, 0.f);
+            if (resok) res = *reinterpret_cast<const float2*>(g.Res + (b * g.res_T + rt) * D + n);
+            if (g.mode == 0) {
+                const float2 bb = *reinterpret_cast<const float2*>(g.bias + n);
+                v0 += bb.x; v1 += bb.y;
+                v0 = g.nonlin == 0 ? tanhf(v0) : fmaxf(v0, 0.f);
+                v1 = g.nonlin == 0 ? tanhf(v1) : fmaxf(v1, 0.f);
+                *reinterpret_cast<float2*>(g.Aout + m * D + n) = make_float2(v0, v1);
+            }
+            float2 o = make_float2(v0 + res.x, v1 + res.y);
+            if (g.accumulate) {
+                const float2 old = *reinterpret_cast<const float2*>(g.Out + m * D + n);
+                o.x += old.x; o.y += old.y;
+            }
+            *reinterpret_cast<float2*>(g.Out + m * D + n) = o;
         }
-        float4 o = make_float4(v[0] + res.x, v[1] + res.y, v[2] + res.z, v[3] + res.w);
-        if (g.accumulate) {
-            const float4 old = ld4(g.Out + m * D + n);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        st4(g.Out + m * D + n, o);
     }
 }
 
@@ -520,10 +563,11 @@ struct ConvDw {
 };
 
 __global__ void __launch_bounds__(256) conv_dw_kernel(ConvDw g) {
-    __shared__ float As[GK][GM];   // [pos][i]
-    __shared__ float Bs[GK][GN];   // [pos][o]
+    __shared__ float As[GK][TS];   // [pos][i]
+    __shared__ float Bs[GK][TS];   // [pos][o]
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
     const int D = g.D;
     const int tiles_n = (D + GN - 1) / GN;
     const int i0 = (blockIdx.x / tiles_n) * GM, o0 = (blockIdx.x % tiles_n) * GN;
@@ -548,25 +592,25 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(ConvDw g) {
         *reinterpret_cast<float4*>(&As[lk][lc]) = av;
         *reinterpret_cast<float4*>(&Bs[lk][lc]) = bv;
         __syncthreads();
+        warp_mma_chunk(As, Bs, wm, wn, lane, acc);
+        if (i0 == 0 && j == 0 && tid < GN) {
 #pragma unroll
-        for (int kk = 0; kk < GK; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float a_[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float b_[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a_[x], b_[y], acc[x][y]);
-            if (i0 == 0 && j == 0 && tid < GN) bacc += Bs[kk][tid];
+            for (int kk = 0; kk < GK; ++kk) bacc += Bs[kk][tid];
         }
     }
     float* out = g.part + ((split * g.k + j) * D) * D;
+    const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const int i = i0 + ty * 4 + x;
-        const int o = o0 + tx * 4;
-        if (i < D && o < D) st4(out + static_cast<int64_t>(i) * D + o, make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]));
+    for (int half = 0; half < 2; ++half) {
+        const int i = i0 + wm * 16 + gq + half * 8;
+        if (i >= D) continue;
+#pragma unroll
+        for (int ns = 0; ns < 4; ++ns) {
+            const int o = o0 + wn * 32 + ns * 8 + 2 * tq;
+            if (o < D)
+                *reinterpret_cast<float2*>(out + static_cast<int64_t>(i) * D + o) =
+                    make_float2(acc[ns][half * 2], acc[ns][half * 2 + 1]);
+        }
     }
     if (i0 == 0 && j == 0 && tid < GN && o0 + tid < D) g.bpart[split * D + o0 + tid] = bacc;
 }
