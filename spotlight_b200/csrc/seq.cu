@@ -22,6 +22,8 @@
 //                        target-role contribution rows, row counts
 //   pool_bwd_kernel      exclusive suffix sums of d r / (count + 1)
 //   seq_fill / seq_reduce  deterministic segmented scatter into dE, dbias
+#include <stdlib.h>
+
 #include "segindex.cuh"
 
 namespace {
@@ -562,6 +564,10 @@ struct ConvDw {
     float* bpart;                 // [splits][D]
 };
 
+}  // namespace
+#include "seq_tc.cuh"
+namespace {
+
 __global__ void __launch_bounds__(256) conv_dw_kernel(ConvDw g) {
     __shared__ float As[GK][TS];   // [pos][i]
     __shared__ float Bs[GK][TS];   // [pos][o]
@@ -689,6 +695,24 @@ int dw_splits(int64_t M, int D, int k) {
     return s;
 }
 
+// tcgen05 path: D == 128 exactly (one 128 x 128 tile spans all channels)
+bool use_tc(int D) {
+    static const bool disabled = getenv("SLB_NO_TCGEN05") != nullptr;
+    return !disabled && D == 128;
+}
+
+int dw_splits_tc(int64_t M, int k) {
+    int s = (2 * 148 + k - 1) / k;
+    const int64_t maxs = (M + tc::KC - 1) / tc::KC;
+    if (s > maxs) s = static_cast<int>(maxs);
+    return s < 1 ? 1 : s;
+}
+
+template <typename K>
+int tc_configure(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
+
 SeqLayout seq_layout(void* base, const slb_seq_step_args* x, bool training) {
     WsCarver ws(base);
     SeqLayout l = {};
@@ -709,7 +733,7 @@ SeqLayout seq_layout(void* base, const slb_seq_step_args* x, bool training) {
             l.A[i] = ws.take<float>(B * T * D);
             l.Y[i] = x->residual ? ws.take<float>(B * T * D) : l.A[i];
             l.Wf[i] = ws.take<float>(static_cast<size_t>(k) * D * D);
-            l.Wb[i] = training ? ws.take<float>(static_cast<size_t>(k) * D * D) : nullptr;
+            l.Wb[i] = (training || use_tc(static_cast<int>(D))) ? ws.take<float>(static_cast<size_t>(k) * D * D) : nullptr;
         }
         if (training) {
             l.dZ = ws.take<float>(B * T * D);
@@ -717,7 +741,8 @@ SeqLayout seq_layout(void* base, const slb_seq_step_args* x, bool training) {
             l.dYb = ws.take<float>(B * T * D);
             size_t part_elems = 0;
             for (int i = 0; i < L; ++i) {
-                const int sp = dw_splits(B * T, static_cast<int>(D), x->kernel_width[i]);
+                const int sp = use_tc(static_cast<int>(D)) ? dw_splits_tc(B * T, x->kernel_width[i])
+                                                           : dw_splits(B * T, static_cast<int>(D), x->kernel_width[i]);
                 l.splits = sp > l.splits ? sp : l.splits;
                 const size_t e = static_cast<size_t>(sp) * x->kernel_width[i] * D * D;
                 part_elems = e > part_elems ? e : part_elems;
@@ -830,9 +855,17 @@ int run_representation(const slb_seq_step_args* x, const SeqLayout& l, float* re
             g.Res = g.In; g.res_T = g.Tin; g.res_shift = i == 0 ? -1 : 0;   // representations.py:404-407, 419-420
         }
         if (!x->residual && !(last && rep_dst)) g.Out = l.A[i];
-        dim3 grid(static_cast<unsigned>((B * T + GM - 1) / GM), static_cast<unsigned>((D + GN - 1) / GN));
-        conv_gemm_kernel<<<grid, 256, 0, st>>>(g);
-        SLB_LAUNCH_CHECK("conv_gemm_kernel(fwd)");
+        if (use_tc(D)) {
+            SLB_REQUIRE(l.Wb[i] != nullptr, "seq: tcgen05 forward needs the [k][out][in] weight copy");
+            g.Wm = l.Wb[i];                                  // [j][n = out][c = in]
+            if (tc_configure(tc::tc_conv_gemm_kernel) != 0) { slb_set_error("seq: cannot configure tcgen05 kernel"); return SLB_ECUDA; }
+            tc::tc_conv_gemm_kernel<<<static_cast<unsigned>((B * T + tc::TM - 1) / tc::TM), 128, tc::SMEM_BYTES, st>>>(g);
+            SLB_LAUNCH_CHECK("tc_conv_gemm_kernel(fwd)");
+        } else {
+            dim3 grid(static_cast<unsigned>((B * T + GM - 1) / GM), static_cast<unsigned>((D + GN - 1) / GN));
+            conv_gemm_kernel<<<grid, 256, 0, st>>>(g);
+            SLB_LAUNCH_CHECK("conv_gemm_kernel(fwd)");
+        }
         *rep_out = g.Out;
     }
     return SLB_OK;
@@ -909,13 +942,22 @@ int slb_seq_train_step(const slb_seq_step_args* x, slb_stream_t stream) {
             conv_shifts(x, i, w.shift, &w.Tin);
             w.In = i == 0 ? l.X0 : l.Y[i - 1];
             w.dZ = l.dZ; w.Tout = T; w.k = k; w.B = B; w.D = D;
-            const int splits = dw_splits(B * T, D, k);
-            w.slab = ((B * T + splits - 1) / splits + GK - 1) / GK * GK;
+            const bool tcp = use_tc(D);
+            const int splits = tcp ? dw_splits_tc(B * T, k) : dw_splits(B * T, D, k);
+            const int slab_q = tcp ? tc::KC : GK;
+            w.slab = ((B * T + splits - 1) / splits + slab_q - 1) / slab_q * slab_q;
             w.part = l.part; w.bpart = l.bpart;
-            dim3 wg(static_cast<unsigned>(((D + GM - 1) / GM) * ((D + GN - 1) / GN)), static_cast<unsigned>(k),
-                    static_cast<unsigned>(splits));
-            conv_dw_kernel<<<wg, 256, 0, st>>>(w);
-            SLB_LAUNCH_CHECK("conv_dw_kernel");
+            if (tcp) {
+                if (tc_configure(tc::tc_conv_dw_kernel) != 0) { slb_set_error("seq: cannot configure tcgen05 kernel"); return SLB_ECUDA; }
+                dim3 wg(static_cast<unsigned>(k), static_cast<unsigned>(splits));
+                tc::tc_conv_dw_kernel<<<wg, 128, tc::SMEM_BYTES, st>>>(w);
+                SLB_LAUNCH_CHECK("tc_conv_dw_kernel");
+            } else {
+                dim3 wg(static_cast<unsigned>(((D + GM - 1) / GM) * ((D + GN - 1) / GN)), static_cast<unsigned>(k),
+                        static_cast<unsigned>(splits));
+                conv_dw_kernel<<<wg, 256, 0, st>>>(w);
+                SLB_LAUNCH_CHECK("conv_dw_kernel");
+            }
             conv_dw_reduce_kernel<<<sq_grid((static_cast<int64_t>(k) * D * D + D + 255) / 256), 256, 0, st>>>(
                 l.part, l.bpart, splits, k, D, x->dconv_w[i], x->dconv_b[i]);
             SLB_LAUNCH_CHECK("conv_dw_reduce_kernel");
@@ -928,9 +970,15 @@ int slb_seq_train_step(const slb_seq_step_args* x, slb_stream_t stream) {
             if (x->residual) { g.Res = dY; g.res_T = T; g.res_shift = i == 0 ? 1 : 0; }
             if (i == 0) { g.Out = l.C; g.accumulate = 1; }      // seq-role rows C[b, s] += d e_s
             else { g.Out = ping; }
-            dim3 grid(static_cast<unsigned>((B * Tin + GM - 1) / GM), static_cast<unsigned>((D + GN - 1) / GN));
-            conv_gemm_kernel<<<grid, 256, 0, st>>>(g);
-            SLB_LAUNCH_CHECK("conv_gemm_kernel(dx)");
+            if (tcp) {
+                g.Wm = l.Wf[i];                              // [j][n = in][c = out]
+                tc::tc_conv_gemm_kernel<<<static_cast<unsigned>((B * Tin + tc::TM - 1) / tc::TM), 128, tc::SMEM_BYTES, st>>>(g);
+                SLB_LAUNCH_CHECK("tc_conv_gemm_kernel(dx)");
+            } else {
+                dim3 grid(static_cast<unsigned>((B * Tin + GM - 1) / GM), static_cast<unsigned>((D + GN - 1) / GN));
+                conv_gemm_kernel<<<grid, 256, 0, st>>>(g);
+                SLB_LAUNCH_CHECK("conv_gemm_kernel(dx)");
+            }
             if (i > 0) { dY = ping; float* tmp = ping; ping = pong; pong = tmp; }
         }
     }
