@@ -34,7 +34,7 @@ def _mask_for(r):
 
 _SCRATCH = {}
 _JUMP = {}
-_PARALLEL_MIN_BLOCKS = 4096     # below this the single-CTA generator is as fast
+_PARALLEL_MIN_BLOCKS = 16384    # below ~10 M words the single-CTA generator beats the 7 jump rounds (~2.5 ms)
 
 
 def _jump_table(dev):
