@@ -7,15 +7,17 @@
 // 115-124, 164-166) and loss.backward() (8x aten::embedding_dense_backward).
 //
 // One kernel per direction:
-//   mf_fwd_kernel  gathers U[u], Q[i+], Q[i-] with 128-bit loads (LPR = D/4
+//   mf_fwd_tile_kernel (mf_fwd_kernel for adaptive hinge)
+//                  gathers U[u], Q[i+], Q[i-] with 128-bit loads (LPR = D/4
 //                  lanes per row, <=32), warp-shuffle dot, loss, d loss/d score,
 //                  emits rank-1 gradient "terms" (user row, item row, g) and
 //                  counts row occurrences with integer atomics.
-//   mf_bwd_kernel  one lane group per touched row: sums g * partner-row over the
-//                  row's terms in ascending term order (deterministic), writes
-//                  the gradient row once (dense or compact).
-// Between them: seg_scan_kernel + mf_fill_kernel build the inverted index
-// (segindex.cuh).  mf_apply_kernel is the optional fused row-wise optimizer.
+//   mf_bwd_tile_kernel  one lane group per touched row: sums g * partner-row over
+//                  the row's terms in ascending term order (deterministic), writes
+//                  the gradient row once (dense or compact), or -- MODE 2 -- applies
+//                  the row-wise optimizer to the user row in place.
+// Between them: seg_tilesum/seg_scan + mf_fill_kernel build the inverted index
+// (segindex.cuh).  mf_apply_kernel is the fused row-wise optimizer for item rows.
 //
 // Algorithmic HBM bytes per interaction (fp32, D = dim, R = 4D):
 //   forward 3R + 3*4 + 3*8, backward re-reads 4R (partner rows), writes <= 3R.
@@ -495,64 +497,6 @@ __global__ void __launch_bounds__(256) mf_fill_kernel(MfDev a) {
     }
 }
 
-template <int LPR>
-__global__ void __launch_bounds__(MF_THREADS) mf_bwd_kernel(MfDev a) {
-    constexpr int GROUPS = MF_THREADS / LPR;
-    constexpr int CAP = seg_sort_cap(LPR);
-    __shared__ int32_t sh_sort[GROUPS * 2 * CAP];
-    const int gl = threadIdx.x & (LPR - 1);
-    const int gib = threadIdx.x / LPR;
-    const unsigned gmask = group_mask(LPR);
-    int32_t* sh = sh_sort + gib * 2 * CAP;
-    const int D = a.D;
-    const int nseg = a.seg.totals[0];
-    const int nsegA = a.seg.totals[2];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
-        a.compact_counts[0] = nsegA;
-        a.compact_counts[1] = nseg - nsegA;
-    }
-    const int32_t* __restrict__ t_a = a.t_a;
-    const int32_t* __restrict__ t_b = a.t_b;
-    const float* __restrict__ t_g = a.t_g;
-
-    for (int64_t s = static_cast<int64_t>(blockIdx.x) * GROUPS + gib; s < nseg;
-         s += static_cast<int64_t>(gridDim.x) * GROUPS) {
-        const int start = a.seg.seg_start[s];
-        const int len = a.seg.seg_start[s + 1] - start;
-        const int64_t row = a.seg.seg_row[s];
-        const bool isA = s < nsegA;
-        const float* partner_tab = isA ? a.Wi : a.Wu;
-        const int32_t* partner_idx = isA ? t_b : t_a;
-        float bacc = 0.f;
-
-        float* out;
-        if (a.grad_mode == SLB_GRAD_DENSE) out = isA ? a.dWu + row * D : a.dWi + (row - a.U) * D;
-        else out = isA ? a.gWu + s * D : a.gWi + (s - nsegA) * D;
-
-        for (int c0 = 0; c0 < D; c0 += LPR * 4) {
-            const int c = c0 + gl * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float b2 = 0.f;
-            seg_visit_sorted<LPR>(a.seg.members, start, len, gl, gmask, sh, [&](int32_t t) {
-                const float g = t_g[t];
-                const float* prow = partner_tab + static_cast<int64_t>(partner_idx[t]) * D;
-                if (c < D) fma4(acc, g, ldg4(prow + c));
-                b2 += g;
-            });
-            if (c < D) st4(out + c, acc);
-            bacc = b2;
-        }
-        if (gl == 0) {
-            if (a.grad_mode == SLB_GRAD_DENSE) {
-                if (isA) a.dbu[row] = bacc; else a.dbi[row - a.U] = bacc;
-            } else {
-                if (isA) { a.urows[s] = row; a.gbu[s] = bacc; }
-                else { a.irows[s - nsegA] = row - a.U; a.gbi[s - nsegA] = bacc; }
-            }
-        }
-    }
-}
-
 // Fused row-wise optimizer over the compact gradient rows (touched rows only).
 // SGD:     W -= lr * (g + wd*W)
 // Adagrad: g' = g + wd*W; state += g'^2; W -= lr * g' / (sqrt(state) + eps)
@@ -936,10 +880,6 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     mf_fill_kernel<<<g1, 256, 0, st>>>(a);
     SLB_LAUNCH_CHECK("mf_fill_kernel");
     const int lpr = lpr_for_dim(dim);
-    const int groups = MF_THREADS / lpr;
-    int64_t bwant = (n + groups - 1) / groups;
-    int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
-    (void)bgrid;
     int64_t tw = ((n + 31) / 32 + 3) / 4;
     int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
     DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);

@@ -189,7 +189,7 @@ __device__ __forceinline__ void seg_place(const SegIndex& s, int64_t key, int32_
 // Hands `visit(term)` the member terms of one segment in ascending term order.
 // G lanes of one group cooperate; all G lanes call with identical (start, len).
 // sh: 2 * seg_sort_cap(G) ints of shared scratch private to the group.
-__host__ __device__ constexpr int seg_sort_cap(int G) { return G >= 4 ? 64 : 16 * G; }
+__host__ __device__ constexpr int seg_sort_cap(int G) { return G >= 8 ? 128 : (G >= 4 ? 64 : 16 * G); }
 
 template <int G, typename F>
 __device__ __forceinline__ void seg_visit_sorted(const int32_t* __restrict__ members, int start,
