@@ -21,6 +21,8 @@
 //
 // Algorithmic HBM bytes per interaction (fp32, D = dim, R = 4D):
 //   forward 3R + 3*4 + 3*8, backward re-reads 4R (partner rows), writes <= 3R.
+#include <stdlib.h>
+
 #include "segindex.cuh"
 
 namespace {
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
         a.compact_counts[0] = nsegA;
         a.compact_counts[1] = nseg - nsegA;
     }
+    if (MODE != 1 && blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;   // hot-row list consumed
     const int seg_lo = MODE == 1 ? nsegA : 0;
     const int seg_hi = MODE == 2 ? nsegA : nseg;
     const int32_t* __restrict__ t_a = a.t_a;
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                         const float gg = t_g[t];
                         fma4(acc, gg, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
                         b2 += gg;
-                    });
+                    }, true);
                 }
                 bacc = b2;
                 if (MODE == 2) {
@@ -699,6 +702,7 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     a.loss_out = loss_out; a.pos_out = x->pos_out; a.neg_out = x->neg_out;
     a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
     a.seg = l.seg;
+    a.seg.long_cap = seg_sort_cap(lpr_for_dim(x->dim));
     a.grad_mode = x->grad_mode;
     a.dWu = x->dWu; a.dWi = x->dWi; a.dbu = x->dbu; a.dbi = x->dbi;
     a.urows = x->urows; a.gWu = x->gWu; a.gbu = x->gbu;
@@ -743,6 +747,8 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     if (phases & 4) {
         mf_fill_kernel<<<fgrid, 256, 0, st>>>(a);
         SLB_LAUNCH_CHECK("mf_fill_kernel");
+        seg_sort_long_kernel<<<SEG_LONG_CTAS, 256, 0, st>>>(a.seg);     // no-op unless hot rows exist
+        SLB_LAUNCH_CHECK("seg_sort_long_kernel");
     }
     int64_t bwant = (2 * B + groups - 1) / groups;
     int bgrid = static_cast<int>(bwant < static_cast<int64_t>(sms) * 8 ? bwant : static_cast<int64_t>(sms) * 8);
@@ -751,9 +757,10 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     const int bti = bsmall ? 8 : 32;
     const int64_t tw = ((2 * B + bti - 1) / bti + 3) / 4;     // upper bound on segment tiles
     const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
-#define BWD_TILE(MODE)                                                                              \
-    if (bsmall) { DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, MODE, 8, tgrid, MF_TILE_THREADS, st, a); } \
-    else { DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, MODE, 32, tgrid, MF_TILE_THREADS, st, a); }
+    const int blpr = lpr;
+#define BWD_TILE(MODE)                                                                               \
+    if (bsmall) { DISPATCH_LPR3(blpr, mf_bwd_tile_kernel, MODE, 8, tgrid, MF_TILE_THREADS, st, a); } \
+    else { DISPATCH_LPR3(blpr, mf_bwd_tile_kernel, MODE, 32, tgrid, MF_TILE_THREADS, st, a); }
     if (x->opt == SLB_OPT_NONE) {
         if (phases & 8) {
             BWD_TILE(0);
@@ -867,6 +874,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     a.Wu = const_cast<float*>(Wu); a.Wi = const_cast<float*>(Wi);
     a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
     a.seg = l.seg;
+    a.seg.long_cap = seg_sort_cap(lpr_for_dim(dim));
     a.grad_mode = SLB_GRAD_DENSE;
     a.dWu = dWu; a.dWi = dWi; a.dbu = dbu; a.dbi = dbi;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -879,6 +887,8 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     SLB_LAUNCH_CHECK("seg_scan_kernel");
     mf_fill_kernel<<<g1, 256, 0, st>>>(a);
     SLB_LAUNCH_CHECK("mf_fill_kernel");
+    seg_sort_long_kernel<<<SEG_LONG_CTAS, 256, 0, st>>>(a.seg);
+    SLB_LAUNCH_CHECK("seg_sort_long_kernel");
     const int lpr = lpr_for_dim(dim);
     int64_t tw = ((n + 31) / 32 + 3) / 4;
     int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);

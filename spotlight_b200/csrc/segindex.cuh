@@ -22,6 +22,7 @@
 constexpr int SEG_SCAN_THREADS = 256;
 constexpr int SEG_SCAN_ITEMS = 16;
 constexpr int SEG_SCAN_TILE = SEG_SCAN_THREADS * SEG_SCAN_ITEMS;  // 4096
+constexpr int SEG_LONG_CTAS = 8;
 
 struct SegIndex {
     int32_t* cnt;        // [Rpad] zero at rest
@@ -32,6 +33,12 @@ struct SegIndex {
     int32_t* seg_row;    // [Tmax]
     int32_t* seg_start;  // [Tmax + 1]
     int32_t* members;    // [Tmax]
+    // hot rows (segments longer than long_cap): sorted by a dedicated kernel
+    int32_t* long_list;  // [Tmax / 16 + 2] segment ids, totals[3] = count
+    int32_t* long_tmp;   // [Tmax] scratch mirror of members
+    uint32_t* long_bits; // [SEG_LONG_CTAS][2 * long_words] bitmap + word prefix
+    int64_t long_words;  // ceil(Tmax / 32)
+    int32_t long_cap;    // segments with more members than this are "long" (0 = feature off)
     int64_t R;           // key space size
     int64_t Rpad;
     int64_t ntiles;
@@ -53,6 +60,11 @@ static inline SegIndex seg_index_carve(WsCarver& ws, int64_t R, int64_t Tmax) {
     s.seg_row = ws.take<int32_t>(Tmax + 1);
     s.seg_start = ws.take<int32_t>(Tmax + 2);
     s.members = ws.take<int32_t>(Tmax + 1);
+    s.long_list = ws.take<int32_t>(Tmax / 16 + 2);
+    s.long_tmp = ws.take<int32_t>(Tmax + 1);
+    s.long_words = (Tmax + 31) / 32;
+    s.long_bits = ws.take<uint32_t>(static_cast<size_t>(SEG_LONG_CTAS) * 2 * s.long_words);
+    s.long_cap = 0;
     return s;
 }
 
@@ -155,6 +167,7 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
             s.off[row] = static_cast<int32_t>(run);
             s.seg_row[seg] = static_cast<int32_t>(row);
             s.seg_start[seg] = static_cast<int32_t>(run);
+            if (s.long_cap > 0 && c[i] > s.long_cap) s.long_list[atomicAdd(s.totals + 3, 1)] = static_cast<int32_t>(seg);
             run += c[i];
             ++seg;
         }
@@ -164,6 +177,55 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
         s.totals[1] = static_cast<int32_t>(run);
         s.seg_start[seg] = static_cast<int32_t>(run);
         if (RA >= s.Rpad) s.totals[2] = static_cast<int32_t>(seg);
+    }
+}
+
+// Sorts the member lists of the hot rows in place (ascending term id), so the
+// consumers can walk them in order.  Term ids are distinct and < Tmax, so the
+// rank of a member is the number of set bits below it in a bitmap of the
+// segment: bitmap -> per-word prefix popcount (block scan) -> rank.  O(Tmax / 32 +
+// len) per hot row, deterministic.  totals[3] is reset by the consumer chain.
+static __global__ void __launch_bounds__(256) seg_sort_long_kernel(SegIndex s) {
+    __shared__ uint32_t sh_scan[256];
+    const int nlong = s.totals[3];
+    uint32_t* bits = s.long_bits + static_cast<size_t>(blockIdx.x) * 2 * s.long_words;
+    uint32_t* pre = bits + s.long_words;
+    const int W = static_cast<int>(s.long_words);
+    const int per = (W + 255) / 256;
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int seg = s.long_list[li];
+        const int start = s.seg_start[seg];
+        const int len = s.seg_start[seg + 1] - start;
+        for (int w = threadIdx.x; w < W; w += 256) bits[w] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += 256) {
+            const int t = s.members[start + i];
+            atomicOr(bits + (t >> 5), 1u << (t & 31));
+        }
+        __syncthreads();
+        // exclusive prefix of popcounts: thread owns words [lo, hi)
+        const int lo = threadIdx.x * per, hi = lo + per < W ? lo + per : W;
+        uint32_t sum = 0;
+        for (int w = lo; w < hi; ++w) sum += __popc(bits[w]);
+        sh_scan[threadIdx.x] = sum;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const uint32_t v = threadIdx.x >= o ? sh_scan[threadIdx.x - o] : 0u;
+            __syncthreads();
+            sh_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        uint32_t run = sh_scan[threadIdx.x] - sum;
+        for (int w = lo; w < hi; ++w) { pre[w] = run; run += __popc(bits[w]); }
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += 256) {
+            const int t = s.members[start + i];
+            const uint32_t r = pre[t >> 5] + __popc(bits[t >> 5] & ((1u << (t & 31)) - 1u));
+            s.long_tmp[start + r] = t;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += 256) s.members[start + i] = s.long_tmp[start + i];
+        __syncthreads();
     }
 }
 
@@ -177,7 +239,8 @@ static inline void seg_scan_launch(const SegIndex& s, int64_t RA, cudaStream_t s
 __device__ __forceinline__ void seg_rearm(const SegIndex& s) {
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    (void)tid; (void)nth;   // two-launch scan: nothing to re-arm (kept for call-site symmetry)
+    (void)nth;
+    if (tid == 0 && s.long_cap == 0) s.totals[3] = 0;   // (with hot-row sorting on, the consumer resets it)
 }
 
 // members[off[key] + (--cnt[key])] = term.  Afterwards cnt is all-zero again.
@@ -194,7 +257,8 @@ __host__ __device__ constexpr int seg_sort_cap(int G) { return G >= 8 ? 128 : (G
 template <int G, typename F>
 __device__ __forceinline__ void seg_visit_sorted(const int32_t* __restrict__ members, int start,
                                                  int len, int gl /* lane in group */,
-                                                 unsigned gmask, int32_t* sh, F visit) {
+                                                 unsigned gmask, int32_t* sh, F visit,
+                                                 bool long_presorted = false) {
     if (len == 1) {
         visit(members[start]);
         return;
@@ -223,8 +287,12 @@ __device__ __forceinline__ void seg_visit_sorted(const int32_t* __restrict__ mem
         __syncwarp(gmask);
         return;
     }
-    // long segment (hot row): repeated min-selection straight from global
-    // memory.  O(len^2 / G) but correct for any length.
+    if (long_presorted) {            // hot row already sorted by seg_sort_long_kernel
+        for (int i = 0; i < len; ++i) visit(members[start + i]);
+        return;
+    }
+    // long segment without the pre-sort: repeated min-selection straight from
+    // global memory.  O(len^2 / G) but correct for any length.
     int32_t last = -1;
     for (int i = 0; i < len; ++i) {
         int32_t best = 0x7fffffff;

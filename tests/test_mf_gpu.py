@@ -173,6 +173,40 @@ def test_fused_step_hot_rows_and_batch_of_one():
     assert_close(out1[3].cpu().numpy(), ref1['dWu'], 1e-5, what='dWu b1')
 
 
+def test_fused_step_zipf_hot_rows():
+    """Skewed item popularity (Zipf) at a large batch: the hottest item owns tens of
+    thousands of terms.  Hot rows are sorted by the bitmap kernel and must stay
+    correct (vs an fp32 ATen restatement), bit-reproducible and reasonably fast."""
+    import time
+    from spotlight_b200 import ops
+    torch.manual_seed(1)
+    U, I, D, B = 200_000, 20_000, 64, 262_144
+    d = dev()
+    Wu = torch.randn(U, D, device=d) / D
+    Wi = torch.randn(I, D, device=d) / D
+    bu = torch.zeros(U, 1, device=d)
+    bi = torch.zeros(I, 1, device=d)
+    p = 1.0 / torch.arange(1, I + 1, device=d, dtype=torch.float64)
+    items = torch.multinomial(p / p.sum(), B, replacement=True)
+    users = torch.randint(0, U, (B,), device=d)
+    negs = torch.randint(0, I, (B,), device=d)
+    hottest = int(torch.bincount(items).max())
+    assert hottest > 10_000
+    o1 = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 1, 1, False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    o2 = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 1, 1, False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert torch.equal(o1[4], o2[4]) and torch.equal(o1[3], o2[3])
+    u, qi, qj = Wu[users], Wi[items], Wi[negs]
+    s = torch.sigmoid((u * qi).sum(1) - (u * qj).sum(1))
+    gp = -(s * (1 - s)) / B
+    rWi = torch.zeros_like(Wi).index_add_(0, items, gp[:, None] * u).index_add_(0, negs, -gp[:, None] * u)
+    assert_close(o1[4].cpu().numpy(), rWi.cpu().numpy(), 5e-5, what='dWi zipf')
+    assert dt < 0.5, 'hot-row path too slow: %.3f s (hottest item %d terms)' % (dt, hottest)
+
+
 def test_fused_step_full_size_properties():
     """BASELINE config 2 shape (1M users x 100K items x 64, B = 65536):
     bit-reproducible, conservation identities, and agreement with an fp32 ATen
