@@ -45,9 +45,11 @@ class _SeqNetBase(nn.Module):
     def user_representation(self, item_sequences):
         """``(all, final)``: ``all[:, :, t]`` has seen items before ``t``
         (t = 0..S-1), ``final`` has seen the whole sequence."""
-        if not self.fusable():
-            raise NotImplementedError('%s needs a plain ScaledEmbedding(padding_idx=0) with '
-                                      'embedding_dim %% 4 == 0' % type(self).__name__)
+        if not self.fusable() or (torch.is_grad_enabled() and self.item_embeddings.weight.requires_grad):
+            # custom / Bloom item layers, or an external training loop that needs
+            # autograd through the representation: differentiable composition over
+            # this package's embedding op (not the measured path)
+            return self._user_representation_autograd(item_sequences)
         rep = ops.seq_representation(self.item_embeddings.weight.detach(),
                                      item_sequences, self._cnn_spec())
         rep = rep.permute(0, 2, 1)                      # (B, D, S+1) like the reference
@@ -76,6 +78,15 @@ class PoolNet(_SeqNetBase):
                                 else ScaledEmbedding(num_items, embedding_dim,
                                                      padding_idx=PADDING_IDX, sparse=sparse))
         self.item_biases = ZeroEmbedding(num_items, 1, sparse=sparse, padding_idx=PADDING_IDX)
+
+    def _user_representation_autograd(self, item_sequences):
+        # prefix mean with the element-wise non-zero count (representations.py:91-114)
+        emb = self.item_embeddings(item_sequences).permute(0, 2, 1)          # (B, D, S)
+        emb = F.pad(emb, (1, 0))                                             # (B, D, S+1)
+        total = torch.cumsum(emb, 2)
+        count = torch.cumsum((emb != 0.0).float(), 2)
+        rep = total / (count + 1)
+        return rep[:, :, :-1], rep[:, :, -1]
 
 
 class CNNNet(_SeqNetBase):
@@ -108,6 +119,23 @@ class CNNNet(_SeqNetBase):
                            for (_kernel_width, _dilation) in zip(self.kernel_width, self.dilation)]
         for i, layer in enumerate(self.cnn_layers):
             self.add_module('cnn_{}'.format(i), layer)
+
+    def _user_representation_autograd(self, item_sequences):
+        # stacked causal dilated convs (representations.py:385-422)
+        emb = self.item_embeddings(item_sequences).permute(0, 2, 1).unsqueeze(3)   # (B, D, S, 1)
+        kw, dl = list(self.kernel_width), list(self.dilation)
+        rf = kw[0] + (kw[0] - 1) * (dl[0] - 1)
+        x = self.nonlinearity(self.cnn_layers[0](F.pad(emb, (0, 0, rf, 0))))
+        if self.residual_connections:
+            x = x + F.pad(emb, (0, 0, 1, 0))
+        for layer, k, d in zip(self.cnn_layers[1:], kw[1:], dl[1:]):
+            rf = k + (k - 1) * (d - 1)
+            residual = x
+            x = self.nonlinearity(layer(F.pad(x, (0, 0, rf - 1, 0))))
+            if self.residual_connections:
+                x = x + residual
+        x = x.squeeze(3)
+        return x[:, :, :-1], x[:, :, -1]
 
     def _cnn_spec(self):
         return dict(kernel_width=[int(k) for k in self.kernel_width][:len(self.cnn_layers)],

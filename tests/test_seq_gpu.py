@@ -130,5 +130,45 @@ def test_sequence_model_fit_golden(name, loss, rep, capsys):
 
 
 def test_generic_route_pool_bloom_golden():
-    """PoolNet over a BloomEmbedding through the generic autograd route."""
-    pytest.skip('generic sequence route needs a differentiable user_representation (next round)')
+    """PoolNet over a BloomEmbedding through the generic autograd route (Bloom gather
+    / scatter kernels + loss kernel) vs the reference's grads."""
+    from spotlight_b200 import losses
+    from spotlight_b200.layers import BloomEmbedding
+    from spotlight_b200.sequence.representations import PoolNet
+    g = load_golden('pool_pointwise_bloom')
+    I, D = int(g['num_items']), int(g['dim'])
+    emb = BloomEmbedding(I, D, compression_ratio=float(g['bloom_ratio']),
+                         num_hash_functions=int(g['bloom_H']), padding_idx=0)
+    net = PoolNet(I, D, item_embedding_layer=emb)
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')})
+    net = net.to('cuda:0')
+    assert not net.fusable()
+    seqs, negs = t(g['seqs']), t(g['negs'])
+    rep, final = net.user_representation(seqs)
+    pos = net(rep, seqs)
+    neg = net(rep, negs)
+    loss = losses.pointwise_loss(pos, neg, mask=(seqs != 0))
+    loss.backward()
+    assert_close(pos.detach().cpu().numpy(), g['pos'], 1e-5, what='pos')
+    assert_close(neg.detach().cpu().numpy(), g['neg'], 1e-5, what='neg')
+    assert_close(loss.item(), g['loss'], 1e-5, what='loss')
+    assert_close(final.detach().cpu().numpy(), g['final'], 1e-5, what='final')
+    for k, p in net.named_parameters():
+        assert_close(p.grad.cpu().numpy(), g['grad.' + k], 1e-5, atol=1e-7, what=k)
+
+
+def test_sequence_model_bloom_fit_runs():
+    """ImplicitSequenceModel with a Bloom-embedded CNNNet takes the generic route."""
+    from spotlight_b200.interactions import SequenceInteractions
+    from spotlight_b200.layers import BloomEmbedding
+    from spotlight_b200.sequence.implicit import ImplicitSequenceModel
+    from spotlight_b200.sequence.representations import CNNNet
+    rs = np.random.RandomState(0)
+    seqs = rs.randint(1, 200, (64, 8)).astype(np.int32)
+    rep = CNNNet(200, 16, item_embedding_layer=BloomEmbedding(200, 16, compression_ratio=0.5,
+                                                              num_hash_functions=2, padding_idx=0))
+    model = ImplicitSequenceModel(loss='bpr', representation=rep, embedding_dim=16, batch_size=32,
+                                  n_iter=2, use_cuda=True, random_state=np.random.RandomState(1))
+    model.fit(SequenceInteractions(seqs, num_items=200))
+    assert model._route() == 'generic'
+    assert model.predict(seqs[0]).shape == (200,)
