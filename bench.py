@@ -406,8 +406,16 @@ def main_ours(a):
     dom = max(alg, key=lambda k: kb[k])
     achieved = alg[dom] * B / (kb[dom] * 1e-3) / 1e9
     step_ms = sum(kb.values())
+    traffic = None
+    try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01e.json')))
+        if tr['batch'] == B and tr['dim'] == a.dim:
+            traffic = tr['dram_bytes_per_launch'].get(dom)
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None,
+                'frac': achieved / peak, 'traffic': traffic,
+                'algorithmic_bytes_per_launch': alg[dom] * B,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650',
                 'algorithmic_bytes_per_interaction': alg[dom],
                 'kernel_ms': kb,
