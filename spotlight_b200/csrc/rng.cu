@@ -274,8 +274,9 @@ int slb_mt19937_fill_parallel(uint32_t* blocks, int64_t nblocks, const uint32_t*
     SLB_REQUIRE(blocks && jump_table && states && nblocks >= 1, "mt19937_fill_parallel: bad arguments");
     if (nblocks == 1) return SLB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // stride J = 2^k blocks per CTA, at most 128 CTAs
-    int k = 0;
+    // stride J = 2^k blocks per CTA: at most 128 CTAs, and at least 1024 blocks per
+    // CTA (a jump round costs about as much as generating ~1000 blocks)
+    int k = 10;
     while (((nblocks - 1 + (1ll << k) - 1) >> k) > 128) ++k;
     const int64_t J = 1ll << k;
     const int P = static_cast<int>((nblocks - 1 + J - 1) / J);

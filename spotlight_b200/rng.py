@@ -34,7 +34,7 @@ def _mask_for(r):
 
 _SCRATCH = {}
 _JUMP = {}
-_PARALLEL_MIN_BLOCKS = 16384    # below ~10 M words the single-CTA generator beats the 7 jump rounds (~2.5 ms)
+_PARALLEL_MIN_BLOCKS = 2048     # >= 2 slices of 1024 blocks: one jump round (~0.35 ms) already pays
 
 
 def _jump_table(dev):
