@@ -30,6 +30,7 @@ EXPORTS = (
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_compact_rows',
     'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch',
+    'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
     'slb_unique_workspace_bytes', 'slb_unique_bucket',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
     'slb_seq_step_workspace_bytes', 'slb_seq_train_step', 'slb_seq_representation',
@@ -53,6 +54,17 @@ class MfStepArgs(ctypes.Structure):
         ('state_Wu', c_vp), ('state_Wi', c_vp), ('state_bu', c_vp), ('state_bi', c_vp),
         ('norm_batch', c_i64), ('opt_users_only', c_i32),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
+    ]
+
+
+class MfBloomArgs(ctypes.Structure):
+    """struct slb_mf_bloom_args."""
+    _fields_ = [
+        ('base', MfStepArgs),
+        ('user_rows', c_i64), ('item_rows', c_i64),
+        ('user_hashes', c_i32), ('item_hashes', c_i32),
+        ('user_seeds', ctypes.c_uint32 * 24), ('item_seeds', ctypes.c_uint32 * 24),
+        ('user_padding_idx', c_i64), ('item_padding_idx', c_i64),
     ]
 
 
@@ -106,6 +118,9 @@ def _declare(lib):
     lib.slb_mf_compact_rows.restype = c_i64
     lib.slb_mf_train_step.argtypes = [P(MfStepArgs), c_vp]
     lib.slb_mf_train_step_phases.argtypes = [P(MfStepArgs), c_i32, c_vp]
+    lib.slb_mf_bloom_workspace_bytes.argtypes = [P(MfBloomArgs)]
+    lib.slb_mf_bloom_workspace_bytes.restype = c_sz
+    lib.slb_mf_bloom_train_step.argtypes = [P(MfBloomArgs), c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
     lib.slb_unique_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_unique_workspace_bytes.restype = c_sz

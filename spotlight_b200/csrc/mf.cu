@@ -52,6 +52,9 @@ struct MfDev {
     int32_t* compact_counts;
     int32_t opt; float lr, wd, eps;
     float* sWu; float* sWi; float* sbu; float* sbi;
+    // hashed-table mode: bias grads are handled outside the segments; frozen rows get no grad
+    int32_t no_bias;
+    int64_t frozen_a, frozen_b;     // table rows that receive no gradient (-1 = none)
 };
 
 template <int LPR>
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
             const bool sA = s < nsegA;
             const float* ptab = sA ? a.Wi : a.Wu;
             const int64_t orow = sA ? s_row : s_row - a.U;
+            if (orow == (sA ? a.frozen_a : a.frozen_b)) continue;     // padding row: no gradient
             float* out = nullptr;
             if (MODE != 2) {
                 if (a.grad_mode == SLB_GRAD_DENSE) out = (sA ? a.dWu : a.dWi) + orow * D;
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                 }
             }
             if (n_gen) __syncwarp(gmask);        // scratch is reused by the next segment
-            if (gl == 0) {
+            if (gl == 0 && !a.no_bias) {
                 if (MODE == 2) {
                     float* bw = a.bu + orow;
                     const float gb = bacc + a.wd * *bw;
@@ -590,6 +594,128 @@ mf_terms_kernel(MfDev a, const float* __restrict__ gscores, int user_broadcast) 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Forward for hashed (Bloom) tables: one lane group per interaction.  The user /
+// item vectors are sums of H hashed rows (layers.py:240-241); the score is the dot
+// of the two sums.  Emits Hu' * Hi' rank-1 terms per side (every pair of a hashed
+// user row and a hashed item row), the id-space bias gradient terms, and the row
+// counts.  Adaptive hinge keeps the reference's user/negative pairing
+// (implicit.py:266-275).
+// ---------------------------------------------------------------------------
+struct BloomSpec {
+    int Hu, Hi;                 // 0 = plain table
+    int64_t pad_u, pad_i;
+    uint32_t su[24], si[24];
+    int64_t num_users, num_items;   // id spaces (bias tables)
+    int64_t* ids_u2; int64_t* ids_i2;   // [2B] bias scatter ids
+    float* g_u2; float* g_i2;           // [2B] bias scatter values
+};
+
+__device__ __forceinline__ int64_t hashed_row(int64_t id, int k, int H, const uint32_t* seeds,
+                                              int64_t rows, int64_t pad) {
+    return H == 0 ? id : bloom_row(id, seeds[k], rows, pad);
+}
+
+template <int LPR>
+__device__ __forceinline__ float bloom_dot(const MfDev& a, const BloomSpec& h, int64_t u, int64_t i,
+                                           int gl, unsigned gmask) {
+    const int D = a.D;
+    const int nu = h.Hu ? h.Hu : 1, ni = h.Hi ? h.Hi : 1;
+    float acc = 0.f;
+    for (int c = gl * 4; c < D; c += LPR * 4) {
+        float4 us = make_float4(0, 0, 0, 0), is = make_float4(0, 0, 0, 0);
+        for (int k = 0; k < nu; ++k) {
+            const float4 v = ldg4(a.Wu + hashed_row(u, k, h.Hu, h.su, a.U, h.pad_u) * D + c);
+            us.x += v.x; us.y += v.y; us.z += v.z; us.w += v.w;
+        }
+        for (int k = 0; k < ni; ++k) {
+            const float4 v = ldg4(a.Wi + hashed_row(i, k, h.Hi, h.si, a.I, h.pad_i) * D + c);
+            is.x += v.x; is.y += v.y; is.z += v.z; is.w += v.w;
+        }
+        acc += dot4(us, is);
+    }
+    return group_sum<LPR>(acc, gmask);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(MF_THREADS) mf_fwd_bloom_kernel(MfDev a, const __grid_constant__ BloomSpec h) {
+    __shared__ float sh_red[MF_THREADS / 32];
+    __shared__ bool is_last;
+    const int gl = threadIdx.x & (LPR - 1);
+    const unsigned gmask = group_mask(LPR);
+    constexpr int GROUPS = MF_THREADS / LPR;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / LPR;
+    const int64_t gstride = static_cast<int64_t>(gridDim.x) * GROUPS;
+    const float invB = 1.0f / static_cast<float>(a.NB);
+    const int nu = h.Hu ? h.Hu : 1, ni = h.Hi ? h.Hi : 1;
+    const int pairs = nu * ni;
+    float lsum = 0.f;
+    const int64_t iters = (a.B + gstride - 1) / gstride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t b = gid + it * gstride;
+        const bool valid = b < a.B;
+        const int64_t bb = valid ? b : 0;
+        int64_t u = a.users[bb], i = a.items[bb];
+        bool bad = u < 0 || u >= h.num_users || i < 0 || i >= h.num_items;
+        if (bad) { u = 0; i = 0; }
+        const float p = bloom_dot<LPR>(a, h, u, i, gl, gmask) + __ldg(a.bu + u) + __ldg(a.bi + i);
+        float n = -INFINITY;
+        int64_t nuid = u, njid = 0;
+        for (int k = 0; k < a.n_neg; ++k) {
+            const int64_t f = static_cast<int64_t>(k) * a.B + bb;
+            int64_t u2 = a.loss == SLB_LOSS_ADAPTIVE_HINGE ? a.users[f / a.n_neg] : u;
+            int64_t j = a.negs[f];
+            if (u2 < 0 || u2 >= h.num_users || j < 0 || j >= h.num_items) { bad = true; u2 = 0; j = 0; }
+            const float nk = bloom_dot<LPR>(a, h, u2, j, gl, gmask) + __ldg(a.bu + u2) + __ldg(a.bi + j);
+            if (valid && gl == 0 && a.neg_out) a.neg_out[f] = nk;
+            if (k == 0 || nk > n) { n = nk; nuid = u2; njid = j; }
+        }
+        if (valid && gl == 0) {
+            if (bad) atomicExch(a.err, 1);
+            float per, gp, gn;
+            pair_loss(a.loss, p, n, per, gp, gn);
+            lsum += per;
+            gp *= invB; gn *= invB;
+            if (bad) { gp = 0.f; gn = 0.f; }
+            if (a.pos_out) a.pos_out[bb] = p;
+            h.ids_u2[bb] = u; h.g_u2[bb] = gp;
+            h.ids_u2[a.B + bb] = nuid; h.g_u2[a.B + bb] = gn;
+            h.ids_i2[bb] = i; h.g_i2[bb] = gp;
+            h.ids_i2[a.B + bb] = njid; h.g_i2[a.B + bb] = gn;
+            const int64_t t0 = bb * 2 * pairs;
+            for (int side = 0; side < 2; ++side) {
+                const float g = side ? gn : gp;
+                const int64_t uu = side ? nuid : u, ii = side ? njid : i;
+                for (int ku = 0; ku < nu; ++ku) {
+                    const int32_t ra = static_cast<int32_t>(hashed_row(uu, ku, h.Hu, h.su, a.U, h.pad_u));
+                    for (int ki = 0; ki < ni; ++ki) {
+                        const int32_t rb = static_cast<int32_t>(hashed_row(ii, ki, h.Hi, h.si, a.I, h.pad_i));
+                        const int64_t t = t0 + side * pairs + ku * ni + ki;
+                        a.t_a[t] = ra; a.t_b[t] = rb; a.t_g[t] = g;
+                        if (g != 0.f) { atomicAdd(a.seg.cnt + ra, 1); atomicAdd(a.seg.cnt + a.U + rb, 1); }
+                    }
+                }
+            }
+        }
+    }
+    const float bsum = block_sum<MF_THREADS>(lsum, sh_red);
+    if (threadIdx.x == 0) {
+        a.partial[blockIdx.x] = bsum;
+        __threadfence();
+        is_last = atomicAdd(a.done, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        float v = 0.f;
+        for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += 32)
+            v += *reinterpret_cast<volatile float*>(a.partial + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) { *a.loss_out = v * invB; *a.done = 0; }
+    }
+}
+
 struct MfLayout {
     int32_t* t_a; int32_t* t_b; float* t_g; float* partial; int32_t* done; int32_t* err;
     SegIndex seg;
@@ -703,6 +829,7 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
     a.seg = l.seg;
     a.seg.long_cap = seg_sort_cap(lpr_for_dim(x->dim));
+    a.no_bias = 0; a.frozen_a = -1; a.frozen_b = -1;
     a.grad_mode = x->grad_mode;
     a.dWu = x->dWu; a.dWi = x->dWi; a.dbu = x->dbu; a.dbi = x->dbi;
     a.urows = x->urows; a.gWu = x->gWu; a.gbu = x->gbu;
@@ -875,6 +1002,7 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
     a.seg = l.seg;
     a.seg.long_cap = seg_sort_cap(lpr_for_dim(dim));
+    a.no_bias = 0; a.frozen_a = -1; a.frozen_b = -1;
     a.grad_mode = SLB_GRAD_DENSE;
     a.dWu = dWu; a.dWi = dWi; a.dbu = dbu; a.dbi = dbi;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -895,6 +1023,128 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     return SLB_OK;
+}
+
+}  // extern "C"
+
+struct BloomLayout {
+    int32_t* t_a; int32_t* t_b; float* t_g; float* partial; int32_t* done; int32_t* err;
+    SegIndex seg;
+    int64_t* ids_u2; int64_t* ids_i2; float* g_u2; float* g_i2;
+    void* ws_u; size_t ws_u_bytes; void* ws_i; size_t ws_i_bytes;
+    size_t bytes;
+};
+
+static BloomLayout bloom_layout(void* base, const slb_mf_bloom_args* x) {
+    const int nu = x->user_hashes ? x->user_hashes : 1, ni = x->item_hashes ? x->item_hashes : 1;
+    const int64_t B = x->base.batch, T = 2 * B * nu * ni;
+    WsCarver ws(base);
+    BloomLayout l;
+    l.done = ws.take<int32_t>(8);
+    l.err = l.done + 4;
+    l.seg = seg_index_carve(ws, x->user_rows + x->item_rows, 2 * T);
+    l.t_a = ws.take<int32_t>(T);
+    l.t_b = ws.take<int32_t>(T);
+    l.t_g = ws.take<float>(T);
+    l.partial = ws.take<float>(MF_MAX_GRID);
+    l.ids_u2 = ws.take<int64_t>(2 * B);
+    l.ids_i2 = ws.take<int64_t>(2 * B);
+    l.g_u2 = ws.take<float>(2 * B);
+    l.g_i2 = ws.take<float>(2 * B);
+    l.ws_u_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_users);
+    l.ws_u = ws.take<char>(l.ws_u_bytes);
+    l.ws_i_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_items);
+    l.ws_i = ws.take<char>(l.ws_i_bytes);
+    l.bytes = ws.bytes();
+    return l;
+}
+
+extern "C" {
+
+size_t slb_mf_bloom_workspace_bytes(const slb_mf_bloom_args* x) {
+    if (!x || x->base.batch <= 0) return 0;
+    return bloom_layout(nullptr, x).bytes;
+}
+
+int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
+    SLB_REQUIRE(x != nullptr, "mf_bloom_train_step: null args");
+    const slb_mf_step_args& b = x->base;
+    SLB_REQUIRE(b.batch > 0 && b.dim >= 4 && b.dim % 4 == 0, "mf_bloom_train_step: bad batch / dim");
+    SLB_REQUIRE(b.loss >= 0 && b.loss <= 3 && b.n_neg >= 1, "mf_bloom_train_step: bad loss / n_neg");
+    SLB_REQUIRE(b.loss == SLB_LOSS_ADAPTIVE_HINGE || b.n_neg == 1, "mf_bloom_train_step: n_neg > 1 only for adaptive hinge");
+    SLB_REQUIRE(b.grad_mode == SLB_GRAD_DENSE && b.opt == SLB_OPT_NONE, "mf_bloom_train_step: dense gradients, no fused optimizer");
+    SLB_REQUIRE(x->user_hashes >= 0 && x->user_hashes <= 24 && x->item_hashes >= 0 && x->item_hashes <= 24,
+                "mf_bloom_train_step: at most 24 hash functions");
+    SLB_REQUIRE(x->user_rows > 0 && x->item_rows > 0 && b.num_users > 0 && b.num_items > 0, "mf_bloom_train_step: empty tables");
+    SLB_REQUIRE(x->user_hashes > 0 || x->user_rows == b.num_users, "mf_bloom_train_step: plain user table must have num_users rows");
+    SLB_REQUIRE(x->item_hashes > 0 || x->item_rows == b.num_items, "mf_bloom_train_step: plain item table must have num_items rows");
+    SLB_REQUIRE(b.users && b.items && b.negs && b.Wu && b.Wi && b.bu && b.bi && b.loss_out && b.dWu && b.dWi && b.dbu && b.dbi && b.workspace,
+                "mf_bloom_train_step: null pointer");
+    const int nu = x->user_hashes ? x->user_hashes : 1, ni = x->item_hashes ? x->item_hashes : 1;
+    const int64_t B = b.batch, T = 2 * B * nu * ni;
+    SLB_REQUIRE(x->user_rows + x->item_rows < (1ll << 31) - SEG_SCAN_TILE && 2 * T < (1ll << 31),
+                "mf_bloom_train_step: too large");
+    BloomLayout l = bloom_layout(b.workspace, x);
+    if (b.workspace_bytes < l.bytes) {
+        slb_set_error("mf_bloom_train_step: workspace too small (%zu < %zu)", b.workspace_bytes, l.bytes);
+        return SLB_ENOSPC;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MfDev a = {};
+    a.B = B; a.NB = b.norm_batch > 0 ? b.norm_batch : B; a.T = T;
+    a.users = b.users; a.items = b.items; a.negs = b.negs; a.loss = b.loss; a.n_neg = b.n_neg;
+    a.U = x->user_rows; a.I = x->item_rows; a.D = b.dim;      // key spaces = table rows
+    a.Wu = b.Wu; a.Wi = b.Wi; a.bu = b.bu; a.bi = b.bi;
+    a.loss_out = b.loss_out; a.pos_out = b.pos_out; a.neg_out = b.neg_out;
+    a.t_a = l.t_a; a.t_b = l.t_b; a.t_g = l.t_g; a.partial = l.partial; a.done = l.done; a.err = l.err;
+    a.seg = l.seg;
+    const int lpr = lpr_for_dim(b.dim);
+    a.seg.long_cap = seg_sort_cap(lpr);
+    a.grad_mode = SLB_GRAD_DENSE;
+    a.dWu = b.dWu; a.dWi = b.dWi; a.dbu = b.dbu; a.dbi = b.dbi;
+    a.no_bias = 1;
+    a.frozen_a = x->user_hashes ? x->user_padding_idx : -1;
+    a.frozen_b = x->item_hashes ? x->item_padding_idx : -1;
+    BloomSpec h = {};
+    h.Hu = x->user_hashes; h.Hi = x->item_hashes;
+    h.pad_u = x->user_padding_idx; h.pad_i = x->item_padding_idx;
+    for (int k = 0; k < 24; ++k) { h.su[k] = x->user_seeds[k]; h.si[k] = x->item_seeds[k]; }
+    h.num_users = b.num_users; h.num_items = b.num_items;
+    h.ids_u2 = l.ids_u2; h.ids_i2 = l.ids_i2; h.g_u2 = l.g_u2; h.g_i2 = l.g_i2;
+
+    const int groups = MF_THREADS / lpr;
+    const int sms = slb_sms();
+    int64_t want = (B + groups - 1) / groups;
+    int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 8 ? want : static_cast<int64_t>(sms) * 8);
+    if (grid > MF_MAX_GRID) grid = MF_MAX_GRID;
+    switch (lpr) {
+        case 1: mf_fwd_bloom_kernel<1><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+        case 2: mf_fwd_bloom_kernel<2><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+        case 4: mf_fwd_bloom_kernel<4><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+        case 8: mf_fwd_bloom_kernel<8><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+        case 16: mf_fwd_bloom_kernel<16><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+        default: mf_fwd_bloom_kernel<32><<<grid, MF_THREADS, 0, st>>>(a, h); break;
+    }
+    SLB_LAUNCH_CHECK("mf_fwd_bloom_kernel");
+    seg_scan_launch(a.seg, a.U, st);
+    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    int fgrid = static_cast<int>((T + 255) / 256);
+    if (fgrid > sms * 8) fgrid = sms * 8;
+    mf_fill_kernel<<<fgrid, 256, 0, st>>>(a);
+    SLB_LAUNCH_CHECK("mf_fill_kernel");
+    seg_sort_long_kernel<<<SEG_LONG_CTAS, 256, 0, st>>>(a.seg);
+    SLB_LAUNCH_CHECK("seg_sort_long_kernel");
+    const int64_t tw = ((2 * T + 31) / 32 + 3) / 4;
+    const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+    DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
+    // id-space bias gradients: deterministic scalar scatter (D = 1)
+    int rc = slb_embedding_backward(l.g_u2, l.ids_u2, 2 * B, 0, nullptr, b.num_users, 1, -1, b.dbu, l.ws_u,
+                                    l.ws_u_bytes, stream);
+    if (rc != SLB_OK) return rc;
+    rc = slb_embedding_backward(l.g_i2, l.ids_i2, 2 * B, 0, nullptr, b.num_items, 1, -1, b.dbi, l.ws_i,
+                                l.ws_i_bytes, stream);
+    return rc;
 }
 
 }  // extern "C"

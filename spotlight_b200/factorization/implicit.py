@@ -151,6 +151,8 @@ class ImplicitFactorizationModel(object):
             return 'epoch'
         if fusable and not self._sparse:
             return 'fused'
+        if isinstance(net, BilinearNet) and not self._sparse and net.fused_spec() is not None:
+            return 'bloom'
         return 'generic'
 
     def _n_neg(self):
@@ -202,7 +204,7 @@ class ImplicitFactorizationModel(object):
             else:
                 negatives = self._epoch_negatives(len(user_ids))
                 epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
-                                                      fused=(route == 'fused'))
+                                                      fused=route)
 
             if verbose:
                 print('Epoch {}: loss {}'.format(epoch_num, epoch_loss))
@@ -324,10 +326,15 @@ class ImplicitFactorizationModel(object):
             batch_neg = negatives[lo * n_neg:(lo + B) * n_neg]
             lo += B
             self._optimizer.zero_grad()
-            if fused:
+            if fused == 'fused':
                 loss = ops.fused_mf_loss(net.user_embeddings.weight, net.item_embeddings.weight,
                                          net.user_biases.weight, net.item_biases.weight,
                                          batch_user, batch_item, batch_neg, self._loss, n_neg)
+            elif fused == 'bloom':
+                spec = net.fused_spec()
+                loss = ops.fused_bloom_loss(spec['Wu'], spec['Wi'], net.user_biases.weight,
+                                            net.item_biases.weight, batch_user, batch_item, batch_neg,
+                                            self._loss, n_neg, spec)
             else:
                 positive_prediction = net(batch_user, batch_item)
                 if self._loss == 'adaptive_hinge':

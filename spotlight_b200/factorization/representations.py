@@ -4,7 +4,7 @@
 import torch.nn as nn
 
 from spotlight_b200 import ops
-from spotlight_b200.layers import ScaledEmbedding, ZeroEmbedding
+from spotlight_b200.layers import BloomEmbedding, ScaledEmbedding, ZeroEmbedding
 
 
 class BilinearNet(nn.Module):
@@ -37,6 +37,22 @@ class BilinearNet(nn.Module):
                     and not layer.sparse and layer.embedding_dim % 4 == 0)
         return (ok(self.user_embeddings) and ok(self.item_embeddings)
                 and not self.user_biases.sparse)
+
+    def fused_spec(self):
+        """Description of the tables for the fused hashed-table training step, or None
+        when a layer is neither a plain ScaledEmbedding nor a BloomEmbedding (or uses
+        sparse gradients): ``dict(Wu, Wi, user_seeds, item_seeds, user_pad, item_pad)``."""
+        def side(layer):
+            if type(layer) is ScaledEmbedding and not layer.sparse and layer.padding_idx is None:
+                return layer.weight, [], -1
+            if type(layer) is BloomEmbedding and not layer.embeddings.sparse:
+                pad = -1 if layer.padding_idx is None else int(layer.padding_idx)
+                return layer.embeddings.weight, list(layer._masks), pad
+            return None
+        u, i = side(self.user_embeddings), side(self.item_embeddings)
+        if u is None or i is None or self.user_biases.sparse or self.embedding_dim % 4 != 0:
+            return None
+        return dict(Wu=u[0], Wi=i[0], user_seeds=u[1], item_seeds=i[1], user_pad=u[2], item_pad=i[2])
 
     def forward(self, user_ids, item_ids):
         """Predictions for (user, item) pairs, shape ``(batch,)``."""

@@ -18,7 +18,7 @@ import torch
 from torch import Tensor
 
 from spotlight_b200 import _lib
-from spotlight_b200._lib import LOSS_KIND, MfStepArgs, SeqStepArgs
+from spotlight_b200._lib import LOSS_KIND, MfBloomArgs, MfStepArgs, SeqStepArgs
 
 # ---------------------------------------------------------------------------
 # plumbing
@@ -292,6 +292,85 @@ def _(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, want_scores):
     return (Wu.new_empty(()), Wu.new_empty((B if want_scores else 0,)),
             Wu.new_empty((B * n_neg if want_scores else 0,)),
             torch.empty_like(Wu), torch.empty_like(Wi), torch.empty_like(bu), torch.empty_like(bi))
+
+
+@torch.library.custom_op('spotlight_b200::mf_bloom_train_step', mutates_args=())
+def mf_bloom_train_step(Wu: Tensor, Wi: Tensor, bu: Tensor, bi: Tensor, users: Tensor, items: Tensor,
+                        negs: Tensor, loss: int, n_neg: int, user_seeds: List[int],
+                        item_seeds: List[int], user_pad: int, item_pad: int, want_scores: bool
+                        ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Fused step for BilinearNet with BloomEmbedding user / item layers (empty seed list
+    = plain table).  Wu / Wi are the (hashed) embedding tables, bu / bi the id-indexed
+    biases.  Returns (loss, pos, neg, dWu, dWi, dbu, dbi), dense."""
+    require_cuda(Wu, Wi, bu, bi, users, items, negs)
+    lib = _lib.load()
+    Wu, Wi, bu, bi = _f32c(Wu), _f32c(Wi), _f32c(bu), _f32c(bi)
+    users, items, negs = _i64c(users).reshape(-1), _i64c(items).reshape(-1), _i64c(negs).reshape(-1)
+    B = users.numel()
+    if items.numel() != B or negs.numel() != B * n_neg:
+        raise ValueError('mf_bloom_train_step: inconsistent batch sizes')
+    dev = Wu.device
+    x = MfBloomArgs()
+    a = x.base
+    a.batch = B
+    a.users, a.items, a.negs = users.data_ptr(), items.data_ptr(), negs.data_ptr()
+    a.loss, a.n_neg = loss, n_neg
+    a.num_users, a.num_items, a.dim = bu.shape[0], bi.shape[0], Wu.shape[1]
+    a.Wu, a.Wi, a.bu, a.bi = Wu.data_ptr(), Wi.data_ptr(), bu.data_ptr(), bi.data_ptr()
+    loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    pos = torch.empty(B if want_scores else 0, dtype=torch.float32, device=dev)
+    neg = torch.empty(B * n_neg if want_scores else 0, dtype=torch.float32, device=dev)
+    dWu, dWi = torch.zeros_like(Wu), torch.zeros_like(Wi)
+    dbu, dbi = torch.zeros_like(bu), torch.zeros_like(bi)
+    a.loss_out = loss_out.data_ptr()
+    if want_scores:
+        a.pos_out, a.neg_out = pos.data_ptr(), neg.data_ptr()
+    a.grad_mode = _lib.GRAD_DENSE
+    a.dWu, a.dWi, a.dbu, a.dbi = dWu.data_ptr(), dWi.data_ptr(), dbu.data_ptr(), dbi.data_ptr()
+    x.user_rows, x.item_rows = Wu.shape[0], Wi.shape[0]
+    x.user_hashes, x.item_hashes = len(user_seeds), len(item_seeds)
+    for k, sd in enumerate(user_seeds):
+        x.user_seeds[k] = int(sd) & 0xFFFFFFFF
+    for k, sd in enumerate(item_seeds):
+        x.item_seeds[k] = int(sd) & 0xFFFFFFFF
+    x.user_padding_idx, x.item_padding_idx = user_pad, item_pad
+    need = lib.slb_mf_bloom_workspace_bytes(ctypes.byref(x))
+    # one workspace per (shapes, batch): its zero-at-rest regions are layout dependent
+    ws = workspace('mfb%d_%d_%d_%d_%d_%d_%d' % (Wu.shape[0], Wi.shape[0], bu.shape[0], bi.shape[0],
+                                                len(user_seeds), len(item_seeds), B), need, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _lib.check(lib.slb_mf_bloom_train_step(ctypes.byref(x), _stream()), 'mf_bloom_train_step')
+    return loss_out.reshape(()), pos, neg, dWu, dWi, dbu, dbi
+
+
+@mf_bloom_train_step.register_fake
+def _(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, user_seeds, item_seeds, user_pad, item_pad,
+      want_scores):
+    B = users.numel()
+    return (Wu.new_empty(()), Wu.new_empty((B if want_scores else 0,)),
+            Wu.new_empty((B * n_neg if want_scores else 0,)),
+            torch.empty_like(Wu), torch.empty_like(Wi), torch.empty_like(bu), torch.empty_like(bi))
+
+
+class _FusedBloomLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Wu, Wi, bu, bi, users, items, negs, loss, n_neg, us, its, up, ip):
+        out = mf_bloom_train_step(Wu.detach(), Wi.detach(), bu.detach(), bi.detach(), users, items,
+                                  negs, loss, n_neg, us, its, up, ip, False)
+        ctx.save_for_backward(*out[3:])
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dWu, dWi, dbu, dbi = ctx.saved_tensors
+        return (dWu * g, dWi * g, dbu * g, dbi * g) + (None,) * 9
+
+
+def fused_bloom_loss(Wu, Wi, bu, bi, users, items, negs, loss: str, n_neg, spec):
+    """As :func:`fused_mf_loss` for hashed tables; ``spec`` from BilinearNet.fused_spec()."""
+    return _FusedBloomLoss.apply(Wu, Wi, bu, bi, users, items, negs, LOSS_KIND[loss], n_neg,
+                                 spec['user_seeds'], spec['item_seeds'], spec['user_pad'],
+                                 spec['item_pad'])
 
 
 class _FusedMFLoss(torch.autograd.Function):

@@ -323,6 +323,82 @@ def test_generic_route_bloom_golden(name, loss):
         assert_close(p.grad.cpu().numpy(), g['grad.' + k], 1e-5, atol=1e-7, what=k)
 
 
+@pytest.mark.parametrize('name,loss', [('mf_hinge_bloom', 'hinge'),
+                                       ('mf_adaptive_bloom', 'adaptive_hinge')])
+def test_fused_bloom_step_golden(name, loss):
+    """The fused hashed-table step (one forward kernel with in-register murmur3, the
+    common deterministic backward, scalar bias scatter) vs the reference's grads."""
+    from spotlight_b200 import ops
+    from spotlight_b200._lib import LOSS_KIND
+    from spotlight_b200.layers import SEEDS
+    g = load_golden(name)
+    H = int(g['bloom_H'])
+    n_neg = int(g['n_neg']) if loss == 'adaptive_hinge' else 1
+    out = ops.mf_bloom_train_step(t(g['sd.user_embeddings.weight']),
+                                  t(g['sd.item_embeddings.embeddings.weight']),
+                                  t(g['sd.user_biases.weight']), t(g['sd.item_biases.weight']),
+                                  t(g['users']), t(g['items']), t(g['negs']), LOSS_KIND[loss], n_neg,
+                                  [], SEEDS[:H], -1, 0, True)
+    l, pos, neg, dWu, dWi, dbu, dbi = [o.cpu().numpy() for o in out]
+    assert_close(pos, g['pos'], 1e-5, what='pos')
+    assert_close(neg.reshape(g['neg'].shape), g['neg'], 1e-5, what='neg')
+    assert_close(l, g['loss'], 1e-5, what='loss')
+    assert_close(dWu, g['grad.user_embeddings.weight'], 1e-5, what='dWu')
+    assert_close(dWi, g['grad.item_embeddings.embeddings.weight'], 1e-5, what='dWi')
+    assert_close(dbu, g['grad.user_biases.weight'], 1e-5, atol=1e-7, what='dbu')
+    assert_close(dbi, g['grad.item_biases.weight'], 1e-5, what='dbi')
+    assert np.all(dWi[0] == 0)          # the padding row of the compressed table is frozen
+
+
+def test_fused_bloom_both_sides_vs_generic_route():
+    """Bloom on users *and* items (the reference's own MF Bloom test shape,
+    tests/factorization/test_implicit.py:127-164): fused step == generic autograd route."""
+    from spotlight_b200 import losses, ops
+    from spotlight_b200.factorization.representations import BilinearNet
+    from spotlight_b200.layers import BloomEmbedding
+    torch.manual_seed(0)
+    U, I, D, B = 300, 500, 32, 512
+    net = BilinearNet(U, I, D, user_embedding_layer=BloomEmbedding(U, D, compression_ratio=0.5,
+                                                                    num_hash_functions=2),
+                      item_embedding_layer=BloomEmbedding(I, D, compression_ratio=0.4,
+                                                          num_hash_functions=3)).to(dev())
+    with torch.no_grad():
+        net.user_biases.weight.normal_(0, 0.1)
+        net.item_biases.weight.normal_(0, 0.1)
+    rs = np.random.RandomState(3)
+    users, items, negs = (t(rs.randint(0, n, B).astype(np.int64)) for n in (U, I, I))
+    spec = net.fused_spec()
+    assert spec is not None and len(spec['user_seeds']) == 2 and len(spec['item_seeds']) == 3
+    lf = ops.fused_bloom_loss(spec['Wu'], spec['Wi'], net.user_biases.weight, net.item_biases.weight,
+                              users, items, negs, 'pointwise', 1, spec)
+    lf.backward()
+    got = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    lg = losses.pointwise_loss(net(users, items), net(users, negs))
+    lg.backward()
+    assert_close(lf.item(), lg.item(), 1e-5, what='loss')
+    for k, p in net.named_parameters():
+        assert_close(got[k].cpu().numpy(), p.grad.cpu().numpy(), 1e-5, atol=1e-8, what=k)
+
+
+def test_model_routes_bloom_through_fused_step():
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    from spotlight_b200.factorization.representations import BilinearNet
+    from spotlight_b200.interactions import Interactions
+    from spotlight_b200.layers import BloomEmbedding, ScaledEmbedding
+    rs = np.random.RandomState(0)
+    inter = Interactions(rs.randint(0, 100, 2000).astype(np.int32), rs.randint(0, 400, 2000).astype(np.int32),
+                         num_users=100, num_items=400)
+    rep = BilinearNet(100, 400, 16, user_embedding_layer=ScaledEmbedding(100, 16),
+                      item_embedding_layer=BloomEmbedding(400, 16, compression_ratio=0.5, num_hash_functions=2))
+    model = ImplicitFactorizationModel(loss='bpr', embedding_dim=16, batch_size=256, n_iter=2,
+                                       representation=rep, use_cuda=True,
+                                       random_state=np.random.RandomState(1))
+    model.fit(inter)
+    assert model._route() == 'bloom'
+    assert model.predict(3).shape == (400,)
+
+
 # ------------------------------------------------------------------- losses
 
 @pytest.mark.parametrize('kind', ['pointwise', 'bpr', 'hinge', 'adaptive_hinge'])
