@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
     const float invB = 1.0f / static_cast<float>(a.NB);
     const int D = a.D;
     float lsum = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;     // hot-row list of the last step
 
     // every group runs the same number of iterations so shuffles stay converged
     const int64_t iters = (a.B + gstride - 1) / gstride;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     const int64_t ntiles = (a.B + TI - 1) / TI;
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
     float lsum = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;     // hot-row list of the last step
 
     for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (MF_TILE_THREADS / 32) + (threadIdx.x >> 5);
          tile < ntiles; tile += wstride) {
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
         a.compact_counts[0] = nsegA;
         a.compact_counts[1] = nseg - nsegA;
     }
-    if (MODE != 1 && blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;   // hot-row list consumed
     const int seg_lo = MODE == 1 ? nsegA : 0;
     const int seg_hi = MODE == 2 ? nsegA : nseg;
     const int32_t* __restrict__ t_a = a.t_a;
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
             const float* ptab = sA ? a.Wi : a.Wu;
             const int64_t orow = sA ? s_row : s_row - a.U;
             if (orow == (sA ? a.frozen_a : a.frozen_b)) continue;     // padding row: no gradient
+            if (s_len > CAP) continue;                                 // hot row: mf_bwd_long_kernel
             float* out = nullptr;
             if (MODE != 2) {
                 if (a.grad_mode == SLB_GRAD_DENSE) out = (sA ? a.dWu : a.dWi) + orow * D;
@@ -438,14 +440,6 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                         fma4(acc, pg[i], ldg4(ptab + static_cast<int64_t>(pp[i]) * D + c));
                         b2 += pg[i];
                     }
-                } else {
-                    // hot row (> CAP terms): ordered selection walk, correct for any length
-                    const int32_t* pidx = sA ? t_b : t_a;
-                    seg_visit_sorted<LPR>(members, s_start, s_len, gl, gmask, sh, [&](int32_t t) {
-                        const float gg = t_g[t];
-                        fma4(acc, gg, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
-                        b2 += gg;
-                    }, true);
                 }
                 bacc = b2;
                 if (MODE == 2) {
@@ -489,6 +483,120 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Hot rows (more terms than the in-group sort capacity).  Their member lists were
+// sorted by seg_sort_long_kernel; one CTA owns one hot row: each of its lane groups
+// walks a contiguous chunk of the sorted members in order, the chunk partials are
+// combined in chunk order.  Same MODE semantics as the tile kernel.
+// ---------------------------------------------------------------------------
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(256) mf_bwd_long_kernel(MfDev a) {
+    constexpr int GROUPS = 256 / LPR;
+    extern __shared__ float sh_part[];            // [GROUPS][D + 4]
+    const int gl = threadIdx.x & (LPR - 1);
+    const int gq = threadIdx.x / LPR;
+    const int D = a.D;
+    const int PS = D + 4;
+    const int nlong = a.seg.totals[3];
+    const int nsegA = a.seg.totals[2];
+    const int32_t* __restrict__ members = a.seg.members;
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int s = a.seg.long_list[li];
+        const bool sA = s < nsegA;
+        if ((MODE == 1 && sA) || (MODE == 2 && !sA)) continue;          // block-uniform
+        const int start = a.seg.seg_start[s];
+        const int len = a.seg.seg_start[s + 1] - start;
+        const int row = a.seg.seg_row[s];
+        const int64_t orow = sA ? row : row - a.U;
+        if (orow == (sA ? a.frozen_a : a.frozen_b)) continue;
+        const float* ptab = sA ? a.Wi : a.Wu;
+        const int32_t* pidx = sA ? a.t_b : a.t_a;
+        const int chunk = (len + GROUPS - 1) / GROUPS;
+        const int lo = min(gq * chunk, len), hi = min(lo + chunk, len);
+        for (int c0 = 0; c0 < D; c0 += LPR * 4) {
+            const int c = c0 + gl * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float b2 = 0.f;
+            int i = lo;
+            for (; i + 4 <= hi; i += 4) {
+                int t[4]; float g[4]; float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k] = members[start + i + k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    g[k] = a.t_g[t[k]];
+                    v[k] = c < D ? ldg4(ptab + static_cast<int64_t>(pidx[t[k]]) * D + c) : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { fma4(acc, g[k], v[k]); b2 += g[k]; }
+            }
+            for (; i < hi; ++i) {
+                const int t = members[start + i];
+                const float g = a.t_g[t];
+                if (c < D) fma4(acc, g, ldg4(ptab + static_cast<int64_t>(pidx[t]) * D + c));
+                b2 += g;
+            }
+            if (c < D) st4(sh_part + gq * PS + c, acc);
+            if (gl == 0 && c0 == 0) sh_part[gq * PS + D] = b2;
+        }
+        __syncthreads();
+        if (gq == 0) {
+            float bacc = 0.f;
+            for (int q = 0; q < GROUPS; ++q) bacc += sh_part[q * PS + D];
+            for (int c = gl * 4; c < D; c += LPR * 4) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < GROUPS; ++q) {
+                    const float4 p = ld4(sh_part + q * PS + c);
+                    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+                }
+                if (MODE == 2) {
+                    float* wrow = a.Wu + orow * D;
+                    float4 w4 = ld4(wrow + c);
+                    float gv[4] = {acc.x + a.wd * w4.x, acc.y + a.wd * w4.y, acc.z + a.wd * w4.z, acc.w + a.wd * w4.w};
+                    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    if (a.opt == SLB_OPT_SGD) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) wv[q] -= a.lr * gv[q];
+                    } else {
+                        float* srow = a.sWu + orow * D;
+                        float4 s4 = ld4(srow + c);
+                        float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { sv[q] += gv[q] * gv[q]; wv[q] -= adagrad_delta(a.lr, gv[q], sv[q], a.eps); }
+                        st4(srow + c, make_float4(sv[0], sv[1], sv[2], sv[3]));
+                    }
+                    st4(wrow + c, make_float4(wv[0], wv[1], wv[2], wv[3]));
+                } else {
+                    float* out;
+                    if (a.grad_mode == SLB_GRAD_DENSE) out = (sA ? a.dWu : a.dWi) + orow * D;
+                    else out = sA ? a.gWu + static_cast<int64_t>(s) * D : a.gWi + static_cast<int64_t>(s - nsegA) * D;
+                    st4(out + c, acc);
+                }
+            }
+            if (gl == 0 && !a.no_bias) {
+                if (MODE == 2) {
+                    float* bw = a.bu + orow;
+                    const float gb = bacc + a.wd * *bw;
+                    if (a.opt == SLB_OPT_SGD) {
+                        *bw -= a.lr * gb;
+                    } else {
+                        float* bs = a.sbu + orow;
+                        const float sv = *bs + gb * gb;
+                        *bs = sv;
+                        *bw -= adagrad_delta(a.lr, gb, sv, a.eps);
+                    }
+                } else if (a.grad_mode == SLB_GRAD_DENSE) {
+                    if (sA) a.dbu[orow] = bacc; else a.dbi[orow] = bacc;
+                } else {
+                    if (sA) { a.urows[s] = orow; a.gbu[s] = bacc; }
+                    else { a.irows[s - nsegA] = orow; a.gbi[s - nsegA] = bacc; }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -585,6 +693,7 @@ mf_scores_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi,
 __global__ void __launch_bounds__(256)
 mf_terms_kernel(MfDev a, const float* __restrict__ gscores, int user_broadcast) {
     const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;
     for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < a.T; t += nth) {
         int64_t u = a.users[user_broadcast ? 0 : t], i = a.items[t];
         float g = gscores[t];
@@ -650,6 +759,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_bloom_kernel(MfDev a, const
     const int nu = h.Hu ? h.Hu : 1, ni = h.Hi ? h.Hi : 1;
     const int pairs = nu * ni;
     float lsum = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.seg.totals[3] = 0;
     const int64_t iters = (a.B + gstride - 1) / gstride;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t b = gid + it * gstride;
@@ -777,6 +887,19 @@ int lpr_for_dim(int D) {
         default: KERNEL<32, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;         \
     }
 
+template <int MODE>
+void launch_long(int lpr, cudaStream_t st, const MfDev& a) {
+    const size_t smem = static_cast<size_t>(256 / lpr) * (a.D + 4) * sizeof(float);
+    switch (lpr) {
+        case 1: mf_bwd_long_kernel<1, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+        case 2: mf_bwd_long_kernel<2, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+        case 4: mf_bwd_long_kernel<4, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+        case 8: mf_bwd_long_kernel<8, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+        case 16: mf_bwd_long_kernel<16, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+        default: mf_bwd_long_kernel<32, MODE><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a); break;
+    }
+}
+
 int validate(const slb_mf_step_args* x) {
     SLB_REQUIRE(x != nullptr, "mf_train_step: null args");
     SLB_REQUIRE(x->batch > 0, "mf_train_step: batch must be > 0");
@@ -892,6 +1015,8 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
         if (phases & 8) {
             BWD_TILE(0);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
+            launch_long<0>(lpr, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_long_kernel");
         }
     } else {
         // fused optimizer: item gradients first (they read the old user rows), then
@@ -899,8 +1024,12 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
         if (phases & 8) {
             BWD_TILE(1);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<items>");
+            launch_long<1>(lpr, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_long_kernel<items>");
             BWD_TILE(2);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
+            launch_long<2>(lpr, st, a);
+            SLB_LAUNCH_CHECK("mf_bwd_long_kernel<users+opt>");
         }
         if ((phases & 16) && !x->opt_users_only) {
             DISPATCH_LPR2(lpr, mf_apply_kernel, 1, bgrid, MF_THREADS, st, a);
@@ -1022,6 +1151,8 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
     int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
     DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
+    launch_long<0>(lpr, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_long_kernel");
     return SLB_OK;
 }
 
@@ -1138,6 +1269,8 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
     DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
+    launch_long<0>(lpr, st, a);
+    SLB_LAUNCH_CHECK("mf_bwd_long_kernel");
     // id-space bias gradients: deterministic scalar scatter (D = 1)
     int rc = slb_embedding_backward(l.g_u2, l.ids_u2, 2 * B, 0, nullptr, b.num_users, 1, -1, b.dbu, l.ws_u,
                                     l.ws_u_bytes, stream);
