@@ -87,7 +87,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -433,7 +433,7 @@ def main_ours(a):
             'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(a, world), 'epoch_loss': epoch_loss,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': K * 7 + n_chunks * 5,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': K * 10 + n_chunks * 12,     # 10 kernels per step + sampler (jump rounds, fill, 4 compaction)
             'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line))
     if world > 1:
