@@ -80,6 +80,7 @@ class SeqStepArgs(ctypes.Structure):
         ('conv_w', c_vp), ('conv_b', c_vp), ('dconv_w', c_vp), ('dconv_b', c_vp),
         ('loss_out', c_vp), ('pos_out', c_vp), ('neg_out', c_vp),
         ('dE', c_vp), ('dbias', c_vp),
+        ('norm_count', c_vp),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
     ]
 

@@ -44,6 +44,7 @@ struct SeqDev {
     int32_t* keys;     // (2*B*S) row id or -1
     float* gs;         // (2*B*S) score grads (bias grads)
     int32_t* hdr;      // [0] done, [1] err, [2] mask count
+    const int32_t* norm;   // optional global mask count (multi-GPU)
     float* partial;
     float* loss_out; float* pos_out; float* neg_out;
     float* dE; float* dbias;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seq_score_kernel(SeqDev a) {
     const unsigned gmask = group_mask(LPR);
     const int D = a.D, S = a.S, T = a.T;
     const int64_t BS = a.B * S, BT = a.B * T;
-    const float msum = static_cast<float>(a.hdr[2]);
+    const float msum = static_cast<float>(a.norm ? *a.norm : a.hdr[2]);
     const float inv = 1.0f / msum;
     const int64_t gid = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / LPR;
     const int64_t gstride = static_cast<int64_t>(gridDim.x) * GROUPS;
@@ -919,7 +920,7 @@ int slb_seq_train_step(const slb_seq_step_args* x, slb_stream_t stream) {
     a.B = B; a.S = S; a.T = T; a.I = x->num_items; a.D = D;
     a.seqs = x->seqs; a.negs = x->negs; a.loss = x->loss; a.n_neg = x->n_neg;
     a.E = x->E; a.bias = x->bias; a.rep = rep; a.dR = l.dR; a.C = l.C; a.keys = l.keys; a.gs = l.gs;
-    a.hdr = l.hdr; a.partial = l.partial;
+    a.hdr = l.hdr; a.partial = l.partial; a.norm = x->norm_count;
     a.loss_out = x->loss_out; a.pos_out = x->pos_out; a.neg_out = x->neg_out;
     a.dE = x->dE; a.dbias = x->dbias; a.seg = l.seg;
     SQ_DISPATCH_LPR(lpr, seq_score_kernel, sq_grid((B * T + groups - 1) / groups), st, a);

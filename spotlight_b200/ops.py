@@ -491,7 +491,7 @@ def seq_step_args(E, bias, seqs, negs, loss, n_neg, cnn=None, keep=None):
     return a, keep
 
 
-def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False):
+def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False, norm_count=None):
     """Fused forward + backward of one sequence minibatch, dense gradients.
 
     Returns dict(loss, pos, neg, dE, dbias, dconv_w, dconv_b).
@@ -515,6 +515,8 @@ def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False
         out['neg'] = torch.empty((n_neg * B, S), dtype=torch.float32, device=dev)
         a.pos_out, a.neg_out = out['pos'].data_ptr(), out['neg'].data_ptr()
     a.dE, a.dbias = out['dE'].data_ptr(), out['dbias'].data_ptr()
+    if norm_count is not None:
+        a.norm_count = norm_count.data_ptr()
     if cnn is not None:
         out['dconv_w'] = [torch.zeros_like(w) for w in cnn['weights']]
         out['dconv_b'] = [torch.zeros_like(b) for b in cnn['biases']]

@@ -122,6 +122,15 @@ class GpuBackend(object):
         adagrad_dense_(st.bi, st.sbi, db.reshape(-1), st.lr, st.eps)
 
 
+    def seq_local_step(self, E_cache, bias_cache, n_cache, seqs_idx, negs_idx, loss, cnn, norm_count):
+        """Fused sequence step on the row cache (ids already remapped onto it; cache
+        row 0 is the padding row).  Returns (loss share, dE_cache, dbias_cache, dconv_w, dconv_b)."""
+        out = ops.seq_train_step(E_cache, bias_cache.reshape(-1, 1), seqs_idx, negs_idx, loss, 1, cnn,
+                                 norm_count=norm_count)
+        return (out['loss'], out['dE'][:n_cache], out['dbias'].reshape(-1)[:n_cache],
+                out['dconv_w'], out['dconv_b'])
+
+
 def adagrad_dense_(W, state, grad, lr, eps):
     """torch.optim.Adagrad update (lr_decay 0) on a small shard; rows with zero
     gradient are unchanged, so this equals the row-wise update of touched rows."""
@@ -255,7 +264,8 @@ class ShardedMF(object):
         local_req = req - st.ilo
         rows, bias = self.backend.gather(st.Wi, st.bi, local_req)
         n_cache = uniq.numel()
-        cap = self.cache_capacity or n_cache
+        # fixed capacity (a function of the batch shape only) so the fused step's workspace is reused
+        cap = self.cache_capacity or min(ids.numel(), plan.num_items)
         cache_rows = self._a2a(rows, recv_counts, send_counts)
         cache_bias = self._a2a(bias, recv_counts, send_counts)
         if cap != n_cache:                 # fixed-capacity cache keeps the kernel workspace layout stable
@@ -274,6 +284,99 @@ class ShardedMF(object):
         gb_recv = self._a2a(g_bias, send_counts, recv_counts)
         self.backend.owner_update(st, local_req, g_recv, gb_recv)
         # 6. global loss
+        total = loss_share.detach().clone().reshape(1)
+        dist.all_reduce(total, group=self.group)
+        return total.reshape(())
+
+
+class SeqShardState(object):
+    """Item-embedding / item-bias shards (+ replicated conv weights) and Adagrad state."""
+
+    def __init__(self, plan, rank, dim, device, lr=0.05, eps=1e-10, init=None, convs=None):
+        ilo, ihi = plan.item_range(rank)
+        self.ilo, self.ihi = ilo, ihi
+        self.lr, self.eps = float(lr), float(eps)
+        dev = torch.device(device)
+        if init is not None:
+            E, bias = init
+            self.Wi = E[ilo:ihi].clone().to(dev)
+            self.bi = bias[ilo:ihi].reshape(-1).clone().to(dev)
+        else:
+            self.Wi = torch.randn((ihi - ilo, dim), device=dev) / dim
+            self.bi = torch.zeros(ihi - ilo, device=dev)
+            if ilo == 0:
+                self.Wi[0] = 0                      # padding row (PADDING_IDX = 0)
+        self.sWi, self.sbi = torch.zeros_like(self.Wi), torch.zeros_like(self.bi)
+        # conv weights are replicated: list of (weight (D,D,k,1), bias (D,)) tensors
+        self.convs = [(w.clone().to(dev), b.clone().to(dev)) for w, b in (convs or [])]
+        self.sconvs = [(torch.zeros_like(w), torch.zeros_like(b)) for w, b in self.convs]
+
+
+class ShardedSeq(object):
+    """PoolNet / CNNNet training step with range-sharded item rows.
+
+    Sequences are data-parallel (each rank owns whole sequences); every item row a
+    rank's batch touches -- as input, target or negative -- is fetched once per step by
+    the same bucket -> all-to-all -> gather -> all-to-all exchange as the MF step, the
+    fused sequence kernels run on the row cache, and the per-row gradients return to
+    their owners.  The loss is normalised by the *global* number of unmasked positions
+    (one scalar all-reduce up front); conv weights are replicated and their gradients
+    all-reduced.
+    """
+
+    def __init__(self, plan, state, rank, backend, cnn=None, group=None, cache_capacity=None):
+        self.plan, self.st, self.rank, self.backend, self.group = plan, state, rank, backend, group
+        self.cnn = cnn                      # dict(kernel_width, dilation, nonlinearity, residual) or None
+        self.cache_capacity = cache_capacity
+        self.stats = {'rows_requested': 0, 'bytes_a2a': 0}
+
+    _a2a = ShardedMF._a2a
+
+    def step(self, seqs, negs, loss):
+        plan, st, P = self.plan, self.st, self.plan.world
+        B, S = seqs.shape
+        dev = seqs.device
+        # global mask count first (device scalar; no host sync)
+        norm = (seqs != 0).sum().to(torch.int32).reshape(1)
+        dist.all_reduce(norm, group=self.group)
+        # distinct ids, with the padding id forced in so that it maps to cache row 0
+        ids = torch.cat([seqs.reshape(-1), negs.reshape(-1), seqs.new_zeros(1)])
+        uniq, inverse, bounds = self.backend.unique_bucket(ids, plan.num_items, plan.ichunk, P)
+        send_counts = [bounds[p + 1] - bounds[p] for p in range(P)]
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        rc = torch.empty(P, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = rc.tolist()
+        req = self._a2a(uniq, send_counts, recv_counts)
+        local_req = req - st.ilo
+        rows, bias = self.backend.gather(st.Wi, st.bi, local_req)
+        n_cache = uniq.numel()
+        # fixed capacity (a function of the batch shape only) so the fused step's workspace is reused
+        cap = self.cache_capacity or min(ids.numel(), plan.num_items)
+        cache_rows = self._a2a(rows, recv_counts, send_counts)
+        cache_bias = self._a2a(bias, recv_counts, send_counts)
+        if cap != n_cache:
+            full = cache_rows.new_zeros((cap, cache_rows.shape[1]))
+            full[:n_cache] = cache_rows
+            fb = cache_bias.new_zeros(cap)
+            fb[:n_cache] = cache_bias
+            cache_rows, cache_bias = full, fb
+        self.stats['rows_requested'] += n_cache
+        cnn = None
+        if self.cnn is not None:
+            cnn = dict(self.cnn, weights=[w for w, _ in st.convs], biases=[b for _, b in st.convs])
+        n = B * S
+        loss_share, g_rows, g_bias, dws, dbs = self.backend.seq_local_step(
+            cache_rows, cache_bias, n_cache, inverse[:n].reshape(B, S), inverse[n:2 * n].reshape(B, S),
+            loss, cnn, norm)
+        g_recv = self._a2a(g_rows.contiguous(), send_counts, recv_counts)
+        gb_recv = self._a2a(g_bias.contiguous(), send_counts, recv_counts)
+        self.backend.owner_update(st, local_req, g_recv, gb_recv)
+        for (w, b), (sw, sb), dw, db in zip(st.convs, st.sconvs, dws, dbs):
+            dist.all_reduce(dw, group=self.group)
+            dist.all_reduce(db, group=self.group)
+            adagrad_dense_(w, sw, dw, st.lr, st.eps)
+            adagrad_dense_(b, sb, db, st.lr, st.eps)
         total = loss_share.detach().clone().reshape(1)
         dist.all_reduce(total, group=self.group)
         return total.reshape(())

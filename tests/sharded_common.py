@@ -7,6 +7,7 @@ import torch
 import torch.distributed as dist
 
 from oracle import mf as omf
+from oracle import seq as oseq
 
 
 class NumpyBackend(object):
@@ -37,6 +38,24 @@ class NumpyBackend(object):
         return (torch.tensor(float(r['loss']) * scale, dtype=torch.float32),
                 torch.from_numpy((r['dWi'] * scale).astype(np.float32))[:n_cache],
                 torch.from_numpy((r['dbi'].reshape(-1) * scale).astype(np.float32))[:n_cache])
+
+    def seq_local_step(self, E_cache, bias_cache, n_cache, seqs_idx, negs_idx, loss, cnn, norm_count):
+        E = E_cache.numpy().astype(np.float64)
+        b = bias_cache.numpy().astype(np.float64).reshape(-1, 1)
+        sq, ng = seqs_idx.numpy(), negs_idx.numpy()
+        if cnn is None:
+            r = oseq.pool_step(E, b, sq, ng, loss, 1, np.float64)
+            dconvs = []
+        else:
+            convs = [(w.numpy().astype(np.float64), c.numpy().astype(np.float64))
+                     for w, c in zip(cnn['weights'], cnn['biases'])]
+            r = oseq.cnn_step(E, b, convs, sq, ng, cnn['kernel_width'], cnn['dilation'], loss, 1,
+                              cnn['nonlinearity'], cnn['residual'], np.float64)
+            dconvs = r['dconvs']
+        scale = float((sq != 0).sum()) / float(norm_count.item())
+        f = lambda x: torch.from_numpy((x * scale).astype(np.float32))      # noqa: E731
+        return (torch.tensor(float(r['loss']) * scale, dtype=torch.float32), f(r['dE'])[:n_cache],
+                f(r['dbias'].reshape(-1))[:n_cache], [f(w) for w, _ in dconvs], [f(c) for _, c in dconvs])
 
     def owner_update(self, st, local_ids, g_rows, g_bias):
         rows = st.Wi.shape[0]
@@ -98,4 +117,67 @@ def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_c
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
         out.append(torch.cat(parts)[:n].cpu().numpy())
+    return out, losses, model.stats
+
+
+def make_seq_problem(seed, I, D, B, S, steps, layers=0, k=3):
+    rs = np.random.RandomState(seed)
+    E = (rs.randn(I, D) * 0.3).astype(np.float32)
+    E[0] = 0
+    bias = (rs.randn(I, 1) * 0.1).astype(np.float32)
+    bias[0] = 0
+    convs = [((rs.randn(D, D, k, 1) * 0.2).astype(np.float32), (rs.randn(D) * 0.1).astype(np.float32))
+             for _ in range(layers)]
+    batches = []
+    for _ in range(steps):
+        seqs = rs.randint(1, I, (B, S)).astype(np.int64)
+        for b in range(B):                       # left padding of ragged length, as to_sequence emits
+            seqs[b, :rs.randint(0, S)] = 0
+        batches.append((seqs, rs.randint(0, I, (B, S)).astype(np.int64)))
+    return (E, bias, convs), batches
+
+
+def seq_oracle_run(params, batches, loss, lr, cnn=None, eps=1e-10):
+    """Single-process reference: full-batch oracle sequence step + dense Adagrad (float64)."""
+    E, bias, convs = params
+    P = [E.astype(np.float64), bias.astype(np.float64)] + [x.astype(np.float64) for wb in convs for x in wb]
+    St = [np.zeros_like(p) for p in P]
+    losses = []
+    for seqs, negs in batches:
+        if cnn is None:
+            r = oseq.pool_step(P[0], P[1], seqs, negs, loss, 1, np.float64)
+            grads = [r['dE'], r['dbias']]
+        else:
+            cv = [(P[2 + 2 * l], P[3 + 2 * l]) for l in range(len(convs))]
+            r = oseq.cnn_step(P[0], P[1], cv, seqs, negs, cnn['kernel_width'], cnn['dilation'], loss, 1,
+                              cnn['nonlinearity'], cnn['residual'], np.float64)
+            grads = [r['dE'], r['dbias']] + [x for wb in r['dconvs'] for x in wb]
+        losses.append(float(r['loss']))
+        for k, g in enumerate(grads):
+            St[k] += g * g
+            P[k] -= lr * g / (np.sqrt(St[k]) + eps)
+    return P, losses
+
+
+def seq_sharded_run(rank, world, params, batches, loss, lr, device, backend, cnn=None):
+    """Sequences are dealt round-robin to ranks; returns (gathered E, bias, convs; losses; stats)."""
+    from spotlight_b200.sharded import SeqShardState, ShardedSeq, ShardPlan
+    E, bias, convs = params
+    I, D = E.shape
+    plan = ShardPlan(1, I, world)
+    st = SeqShardState(plan, rank, D, device, lr=lr, init=(torch.from_numpy(E), torch.from_numpy(bias)),
+                       convs=[(torch.from_numpy(w), torch.from_numpy(b)) for w, b in convs])
+    model = ShardedSeq(plan, st, rank, backend, cnn=cnn)
+    losses = []
+    for seqs, negs in batches:
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x[rank::world])).to(device)   # noqa: E731
+        losses.append(float(model.step(t(seqs), t(negs), loss)))
+    out = []
+    for shard in (st.Wi, st.bi.reshape(-1, 1)):
+        pad = torch.zeros((plan.ichunk,) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        pad[:shard.shape[0]] = shard
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat(parts)[:I].cpu().numpy())
+    out += [x.cpu().numpy() for wb in st.convs for x in wb]
     return out, losses, model.stats

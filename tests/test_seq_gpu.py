@@ -172,3 +172,18 @@ def test_sequence_model_bloom_fit_runs():
     model.fit(SequenceInteractions(seqs, num_items=200))
     assert model._route() == 'generic'
     assert model.predict(seqs[0]).shape == (200,)
+
+
+def test_seq_step_global_norm_count():
+    """Multi-GPU hook: with norm_count = c x (this batch's unmasked count) the loss share
+    and every gradient are the single-rank ones divided by c."""
+    from spotlight_b200 import ops
+    g = load_golden('pool_bpr')
+    E, b = t(g['sd.item_embeddings.weight']), t(g['sd.item_biases.weight'])
+    seqs, negs = t(g['seqs']), t(g['negs'])
+    base = ops.seq_train_step(E, b, seqs, negs, 'bpr', 1, None)
+    norm = ((seqs != 0).sum() * 4).to(torch.int32).reshape(1)
+    out = ops.seq_train_step(E, b, seqs, negs, 'bpr', 1, None, norm_count=norm)
+    assert_close(out['loss'].item() * 4, base['loss'].item(), 1e-6, what='loss')
+    assert_close(out['dE'].cpu().numpy() * 4, base['dE'].cpu().numpy(), 1e-6, what='dE')
+    assert_close(out['dbias'].cpu().numpy() * 4, base['dbias'].cpu().numpy(), 1e-6, what='dbias')

@@ -63,6 +63,53 @@ def test_sharded_step_matches_single_process(world, loss, exchange):
         assert stats['rows_requested'] <= 3 * 57
 
 
+_CNN = dict(kernel_width=[3, 3], dilation=[1, 2], nonlinearity='tanh', residual=True)
+
+
+def _seq_worker(rank, world, port, loss, net, q):
+    import sharded_common as sc
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        cnn = _CNN if net == 'cnn' else None
+        params, batches = sc.make_seq_problem(9, 41, 8, 10, 7, 3, layers=2 if cnn else 0)
+        got, losses, stats = sc.seq_sharded_run(rank, world, params, batches, loss, 0.05, 'cpu',
+                                                sc.NumpyBackend(), cnn=cnn)
+        if rank == 0:
+            q.put((got, losses, stats))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,loss,net', [(2, 'bpr', 'pool'), (3, 'pointwise', 'pool'),
+                                            (2, 'bpr', 'cnn')])
+def test_sharded_sequence_step_matches_single_process(world, loss, net):
+    """Sequence models: sequences are data-parallel, item rows
+    range-sharded and fetched once per step, conv weights replicated + all-reduced,
+    loss normalised by the global unmasked count."""
+    import sharded_common as sc
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world * 11) % 2000
+    procs = [ctx.Process(target=_seq_worker, args=(r, world, port, loss, net, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses, stats = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cnn = _CNN if net == 'cnn' else None
+    params, batches = sc.make_seq_problem(9, 41, 8, 10, 7, 3, layers=2 if cnn else 0)
+    ref, ref_losses = sc.seq_oracle_run(params, batches, loss, 0.05, cnn=cnn)
+    assert_close(np.array(losses), np.array(ref_losses), 1e-5, what='losses')
+    assert len(got) == len(ref)
+    for k, (a, b) in enumerate(zip(got, ref)):
+        assert_close(a, b, 3e-5, what='param%d' % k)
+    assert stats['rows_requested'] <= 3 * 41
+    assert not got[0][0].any() and not got[1][0].any()          # padding row stays zero
+
+
 def test_shard_plan_ranges():
     from spotlight_b200.sharded import ShardPlan
     plan = ShardPlan(10, 7, 4)

@@ -60,3 +60,50 @@ def test_sharded_gpu_matches_oracle(loss, exchange):
         # Adagrad trajectory tolerance: first-touch normalisation amplifies 1e-7 gradient
         # differences on near-cancelling rows (see test_model_gpu / test_sharded_cpu)
         assert_close(a, b, 5e-3, what=nm)
+
+
+_CNN = dict(kernel_width=[3, 3], dilation=[1, 2], nonlinearity='relu', residual=True)
+SEQ_SHAPE = {'pool': (11, 300, 32, 24, 20, 3), 'cnn': (11, 300, 128, 24, 20, 3)}   # seed, I, D, B, S, steps
+
+
+def _seq_worker(rank, world, port, loss, net, q):
+    import sharded_common as sc
+    from spotlight_b200.sharded import GpuBackend
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        cnn = _CNN if net == 'cnn' else None
+        params, batches = sc.make_seq_problem(*SEQ_SHAPE[net], layers=2 if cnn else 0)
+        dev = torch.device('cuda', rank)
+        got, losses, stats = sc.seq_sharded_run(rank, world, params, batches, loss, 0.05, dev,
+                                                GpuBackend(dev), cnn=cnn)
+        if rank == 0:
+            q.put((got, losses, stats))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loss,net', [('bpr', 'pool'), ('pointwise', 'cnn')])
+def test_sharded_sequence_gpu_matches_oracle(loss, net):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import sharded_common as sc
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() * 5) % 2000
+    procs = [ctx.Process(target=_seq_worker, args=(r, world, port, loss, net, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses, stats = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cnn = _CNN if net == 'cnn' else None
+    params, batches = sc.make_seq_problem(*SEQ_SHAPE[net], layers=2 if cnn else 0)
+    ref, ref_losses = sc.seq_oracle_run(params, batches, loss, 0.05, cnn=cnn)
+    assert_close(np.array(losses), np.array(ref_losses), 2e-5, what='losses')
+    for k, (a, b) in enumerate(zip(got, ref)):
+        assert_close(a, b, 5e-3, what='param%d' % k)      # Adagrad trajectory tolerance, as above
