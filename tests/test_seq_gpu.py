@@ -67,9 +67,11 @@ def test_cnn_step_golden(name, loss):
     assert_close(rep[:, -1].cpu().numpy(), g['final'], 1e-5, what='final')
 
 
-@pytest.mark.parametrize('kind', ['pool', 'cnn'])
+@pytest.mark.parametrize('kind', ['pool', 'cnn', 'cnn_relu'])
 @pytest.mark.parametrize('D,S,B', [(128, 200, 16), (64, 33, 40), (256, 7, 9)])
 def test_seq_step_vs_oracle_sizes(kind, D, S, B):
+    nl = 'relu' if kind == 'cnn_relu' else 'tanh'
+    kind = kind.split('_')[0]
     from spotlight_b200 import ops
     rs = np.random.RandomState(D + S)
     I = 500
@@ -86,9 +88,9 @@ def test_seq_step_vs_oracle_sizes(kind, D, S, B):
         W = [(rs.randn(D, D, 3, 1) * 0.05).astype(np.float32), (rs.randn(D, D, 2, 1) * 0.05).astype(np.float32)]
         bb = [(rs.randn(D) * 0.05).astype(np.float32) for _ in W]
         convs = list(zip(W, bb))
-        spec = dict(kernel_width=[3, 2], dilation=[1, 2], nonlinearity='tanh', residual=True,
+        spec = dict(kernel_width=[3, 2], dilation=[1, 2], nonlinearity=nl, residual=True,
                     weights=[t(w) for w in W], biases=[t(x) for x in bb])
-        ref = oseq.cnn_step(E, bias, convs, seqs, negs, [3, 2], [1, 2], 'bpr', 1, 'tanh', True, np.float64)
+        ref = oseq.cnn_step(E, bias, convs, seqs, negs, [3, 2], [1, 2], 'bpr', 1, nl, True, np.float64)
     else:
         ref = oseq.pool_step(E, bias, seqs, negs, 'bpr', 1, np.float64)
     out = ops.seq_train_step(t(E), t(bias), t(seqs), t(negs), 'bpr', 1, spec, want_scores=True)

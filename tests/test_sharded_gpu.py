@@ -62,7 +62,10 @@ def test_sharded_gpu_matches_oracle(loss, exchange):
         assert_close(a, b, 5e-3, what=nm)
 
 
-_CNN = dict(kernel_width=[3, 3], dilation=[1, 2], nonlinearity='relu', residual=True)
+# tanh keeps the scores bounded: with relu at this scale the fp32 sigmoid saturates and a few
+# row gradients underflow to exactly 0 where the float64 oracle keeps 1e-16, which Adagrad's
+# first-touch normalisation turns into a full lr step (fp32 torch underflows the same way)
+_CNN = dict(kernel_width=[3, 3], dilation=[1, 2], nonlinearity='tanh', residual=True)
 SEQ_SHAPE = {'pool': (11, 300, 32, 24, 20, 3), 'cnn': (11, 300, 128, 24, 20, 3)}   # seed, I, D, B, S, steps
 
 
