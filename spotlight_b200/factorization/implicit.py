@@ -32,6 +32,7 @@ from spotlight_b200.factorization._components import _predict_process_ids
 from spotlight_b200.factorization.representations import BilinearNet
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
+from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, shuffled_order_device
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
 
@@ -53,6 +54,10 @@ def _to_device_ids(ids, device):
         arr = arr.astype(np.int64)
     return torch.from_numpy(arr).to(device).long()
 
+
+# epochs at least this long take their permutation from the device shuffle (csrc/shuffle.cu);
+# both paths are bit-exact with numpy, so the threshold is a speed knob only
+DEVICE_SHUFFLE_MIN = 1 << 17
 
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
            'route; construct the model with use_cuda=True.')
@@ -193,8 +198,13 @@ class ImplicitFactorizationModel(object):
         for epoch_num in range(self._n_iter):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
             # (torch_utils.py:46-47); the fancy-index gathers run on the device
-            order = shuffled_order(len(user_ids), self._random_state)
-            order_dev = torch.from_numpy(order).to(device).long()
+            n = len(user_ids)
+            if DEVICE_SHUFFLE_MIN <= n <= SHUFFLE_DEVICE_MAX and \
+                    self._random_state.get_state()[0] == 'MT19937':
+                order_dev = shuffled_order_device(n, self._random_state, device)
+            else:                               # short epochs: the host loop beats the launches
+                order = shuffled_order(n, self._random_state)
+                order_dev = torch.from_numpy(order).to(device).long()
             user_ids_tensor = users_dev.index_select(0, order_dev)
             item_ids_tensor = items_dev.index_select(0, order_dev)
             del order_dev

@@ -143,3 +143,93 @@ def sample_items_device(num_items, shape, random_state, device, out=None):
         key = blocks[blk * _N:(blk + 1) * _N].cpu().numpy().view(np.uint32).copy()
     random_state.set_state(('MT19937', key, pos, 0, 0.0))
     return out.reshape(shape)
+
+
+_GAMMA = 0.5772156649015329
+
+
+def _harmonic(x):
+    if x < 64:
+        return sum(1.0 / k for k in range(1, int(x) + 1))
+    return math.log(x) + _GAMMA + 0.5 / x - 1.0 / (12.0 * x * x)
+
+
+def _shuffle_expected_words(n):
+    """E[stream words consumed by RandomState.shuffle of n elements] = sum_i M(i)/(i+1)."""
+    total, hi = 0.0, n - 1
+    while hi >= 1:
+        M = _mask_for(hi) + 1
+        lo = M // 2
+        total += M * (_harmonic(hi + 1) - _harmonic(lo))
+        hi = lo - 1
+    return total
+
+
+_SHUFFLE_WS = {}
+SHUFFLE_DEVICE_MAX = 1 << 29
+
+
+def shuffled_order_device(n, random_state, device, rounds=24):
+    """``random_state.shuffle(arange(n))`` as an int64 CUDA tensor, computed on the device.
+
+    Bit-exact with NumPy (same permutation, ``random_state`` left in the same state):
+    the stream is generated by the jump-ahead MT19937 kernels, the acceptance pattern of
+    the n-1 masked-rejection draws and the chain of dependent swaps are both resolved in
+    parallel (csrc/shuffle.cu).  Replaces spotlight/torch_utils.py:46-47 for the epoch
+    shuffle of factorization/implicit.py:212-214.
+    """
+    n = int(n)
+    dev = torch.device(device)
+    if n <= 1:
+        return torch.zeros(n, dtype=torch.int64, device=dev)
+    if n > SHUFFLE_DEVICE_MAX:
+        raise ValueError('shuffled_order_device: n must be <= 2**29')
+    lib = _lib.load()
+    st = random_state.get_state()
+    if st[0] != 'MT19937':
+        raise ValueError('shuffled_order_device needs a legacy MT19937 RandomState')
+    key = np.ascontiguousarray(st[1], dtype=np.uint32)
+    pos = int(st[2])
+    order = torch.empty(n, dtype=torch.int64, device=dev)
+    margin = 8.0
+    while True:
+        need_words = _shuffle_expected_words(n) + margin * math.sqrt(2.0 * n) + 64
+        nblocks = int(math.ceil((pos + need_words) / _N)) + 1
+        nwords = nblocks * _N
+        ws_bytes = lib.slb_shuffle_workspace_bytes(n, nwords - pos)
+        blocks, _, _, pin_key, _ = _scratch(dev, nwords, 0)
+        skey = (dev.index if dev.index is not None else torch.cuda.current_device(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        cur = _SHUFFLE_WS.get(skey)
+        if cur is None or cur[0].numel() < ws_bytes:
+            cur = (torch.empty(ws_bytes + 4096, dtype=torch.uint8, device=dev),
+                   torch.empty(4, dtype=torch.int64, device=dev))
+            _SHUFFLE_WS[skey] = cur
+        ws, cursor = cur
+        pin_key.copy_(torch.from_numpy(key.view(np.int32)))
+        blocks[:_N].copy_(pin_key, non_blocking=True)
+        if nblocks >= _PARALLEL_MIN_BLOCKS:
+            table, rows, states = _jump_table(dev)
+            _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
+                                                     _ptr(states), _stream()), 'mt19937_fill_parallel')
+        else:
+            _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
+        resume = 0
+        while True:
+            rc = lib.slb_shuffle_order(_ptr(blocks), nwords, _ptr(cursor), pos, n, int(rounds), resume,
+                                       _ptr(order), _ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, 'shuffle_order')
+            end, swaps, converged, _ = (int(v) for v in cursor.tolist())     # the call's one sync
+            if converged:
+                break
+            resume = 1
+        if swaps == n - 1:
+            break
+        margin *= 4.0                       # stream too short (8-sigma event): regenerate longer
+    if end % _N == 0 and end > 0:           # numpy leaves pos = 624 on a block boundary
+        blk, pos = end // _N - 1, _N
+    else:
+        blk, pos = end // _N, end % _N
+    key = blocks[blk * _N:(blk + 1) * _N].cpu().numpy().view(np.uint32).copy()
+    random_state.set_state(('MT19937', key, pos, st[3], st[4]))
+    return order
