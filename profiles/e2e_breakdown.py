@@ -5,8 +5,8 @@ import argparse, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from spotlight_b200.factorization.implicit import _to_device_ids
-from spotlight_b200.rng import shuffled_order_device
+from spotlight_b200.factorization.implicit import _to_device_narrow
+from spotlight_b200.rng import permute_ids, shuffled_order_device
 from spotlight_b200.torch_utils import shuffled_order
 
 ap = argparse.ArgumentParser(); ap.add_argument('--batch', type=int, default=524288); ap.add_argument('--steps', type=int, default=100)
@@ -24,15 +24,19 @@ def timed(name, fn, reps=2):
         print('%-28s rep %d  %.2f ms' % (name, r, (time.perf_counter() - t0) * 1e3), flush=True)
     return out
 
-timed('check_input', lambda: model._check_input(hu, hi))
-ud = timed('ids H2D + widen (users)', lambda: _to_device_ids(hu, dev))
-idv = timed('ids H2D + widen (items)', lambda: _to_device_ids(hi, dev))
+ud = timed('ids H2D (users)', lambda: _to_device_narrow(hu, dev))
+idv = timed('ids H2D (items)', lambda: _to_device_narrow(hi, dev))
+timed('device id range check', lambda: model._check_input(int(ud.max()), int(idv.max())))
 timed('host shuffle + H2D', lambda: torch.from_numpy(shuffled_order(n, np.random.RandomState(1))).to(dev).long(), reps=1)
 order = timed('device shuffle', lambda: shuffled_order_device(n, np.random.RandomState(1), dev), reps=3)
 ref = np.arange(n); np.random.RandomState(1).shuffle(ref)
 print('device shuffle == numpy:', bool(np.array_equal(order.cpu().numpy(), ref)))
-us = timed('index_select x2', lambda: (ud.index_select(0, order), idv.index_select(0, order)))
+us = timed('permute_ids', lambda: permute_ids(order, ud, idv))
+assert torch.equal(us[0], ud.long()[order]) and torch.equal(us[1], idv.long()[order])
 timed('epoch pipeline (K steps)', lambda: model._run_epoch_device(us[0], us[1]))
+from spotlight_b200.interactions import Interactions
+inter = Interactions(hu, hi, num_users=a.users, num_items=a.items)
+timed('model.fit (1 epoch)', lambda: model.fit(inter), reps=3)
 # kernel-level view of the device shuffle
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:

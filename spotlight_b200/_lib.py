@@ -26,7 +26,7 @@ EXPORTS = (
     'slb_version', 'slb_last_error', 'slb_sm_count', 'slb_workspace_init',
     'slb_mt19937_fill', 'slb_mt19937_fill_parallel', 'slb_host_shuffle_order',
     'slb_sample_workspace_bytes', 'slb_sample_bounded',
-    'slb_shuffle_workspace_bytes', 'slb_shuffle_order',
+    'slb_shuffle_workspace_bytes', 'slb_shuffle_order', 'slb_permute_ids',
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_compact_rows',
@@ -105,6 +105,7 @@ def _declare(lib):
     lib.slb_shuffle_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_shuffle_workspace_bytes.restype = c_sz
     lib.slb_shuffle_order.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]
+    lib.slb_permute_ids.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]
     lib.slb_sample_workspace_bytes.argtypes = [c_i64]
     lib.slb_sample_workspace_bytes.restype = c_sz
     lib.slb_sample_bounded.argtypes = [c_vp, c_i64, c_vp, ctypes.c_uint32, c_i64, c_vp, c_vp, c_sz, c_vp]

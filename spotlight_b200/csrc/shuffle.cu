@@ -359,6 +359,21 @@ __global__ void shuf_final_kernel(int32_t n, const int32_t* __restrict__ jv,
     }
 }
 
+// users_out[i] = users[order[i]], items_out[i] = items[order[i]] (ids widened to int64):
+// the two fancy-index gathers of torch_utils.shuffle (torch_utils.py:49-52) in one pass.
+template <typename T>
+__global__ void permute_ids_kernel(const int64_t* __restrict__ order, int64_t n, const T* __restrict__ a,
+                                   const T* __restrict__ b, int64_t* __restrict__ oa,
+                                   int64_t* __restrict__ ob) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t o = order[i];
+        if (o < 0 || o >= n) { oa[i] = -1; if (b) ob[i] = -1; continue; }     // caught by the id range flags
+        oa[i] = static_cast<int64_t>(__ldg(a + o));
+        if (b) ob[i] = static_cast<int64_t>(__ldg(b + o));
+    }
+}
+
 struct ShufLayout {
     int32_t *start, *prev, *cntT, *flags, *jv, *cnt, *off, *members, *parent, *mlink, *tsum;
     int ntiles, nscan;
@@ -445,6 +460,24 @@ int slb_shuffle_order(const uint32_t* blocks, int64_t nwords, int64_t* cursor, i
     shuf_link_kernel<<<grid_for(n, 256), 256, 0, st>>>(n32, l.off, l.members, l.parent, l.mlink, l.flags);
     shuf_final_kernel<<<grid_for(n, 256), 256, 0, st>>>(n32, l.jv, l.parent, l.mlink, order, l.flags);
     SLB_LAUNCH_CHECK("shuffle stage B");
+    return SLB_OK;
+}
+
+int slb_permute_ids(const int64_t* order, int64_t n, const void* users, const void* items,
+                    int32_t elem_bytes, int64_t* users_out, int64_t* items_out, slb_stream_t stream) {
+    SLB_REQUIRE(n >= 0, "permute_ids: n must be >= 0");
+    if (n == 0) return SLB_OK;
+    SLB_REQUIRE(order && users && users_out, "permute_ids: null pointer");
+    SLB_REQUIRE((items == nullptr) == (items_out == nullptr), "permute_ids: items / items_out mismatch");
+    SLB_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "permute_ids: elem_bytes must be 4 or 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (elem_bytes == 4)
+        permute_ids_kernel<int32_t><<<grid_for(n, 256), 256, 0, st>>>(
+            order, n, static_cast<const int32_t*>(users), static_cast<const int32_t*>(items), users_out, items_out);
+    else
+        permute_ids_kernel<int64_t><<<grid_for(n, 256), 256, 0, st>>>(
+            order, n, static_cast<const int64_t*>(users), static_cast<const int64_t*>(items), users_out, items_out);
+    SLB_LAUNCH_CHECK("permute_ids_kernel");
     return SLB_OK;
 }
 

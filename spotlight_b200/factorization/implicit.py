@@ -32,7 +32,7 @@ from spotlight_b200.factorization._components import _predict_process_ids
 from spotlight_b200.factorization.representations import BilinearNet
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
-from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, shuffled_order_device
+from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, permute_ids, shuffled_order_device
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
 
@@ -49,10 +49,16 @@ def _side_stream(device):
 
 def _to_device_ids(ids, device):
     """Host id array -> int64 CUDA tensor (narrow on the wire, widened on the device)."""
+    return _to_device_narrow(ids, device).long()
+
+
+def _to_device_narrow(ids, device):
+    """Host id array -> CUDA tensor in its own width (int32 stays int32 on the wire and in
+    HBM; the permutation gather widens)."""
     arr = np.ascontiguousarray(ids)
     if arr.dtype not in (np.int32, np.int64):
         arr = arr.astype(np.int64)
-    return torch.from_numpy(arr).to(device).long()
+    return torch.from_numpy(arr).to(device)
 
 
 # epochs at least this long take their permutation from the device shuffle (csrc/shuffle.cu);
@@ -187,13 +193,17 @@ class ImplicitFactorizationModel(object):
         if not self._use_cuda:
             raise RuntimeError(_NO_CPU)
 
-        self._check_input(user_ids, item_ids)
         route = self._route()
         device = self._device()
-        # ids go to the device once per fit(); each epoch only the permutation travels
-        # (the reference re-uploads both shuffled id arrays, implicit.py:216-219)
-        users_dev = _to_device_ids(user_ids, device)
-        items_dev = _to_device_ids(item_ids, device)
+        # ids go to the device once per fit(); each epoch only the permutation is made
+        # there (the reference re-uploads both shuffled id arrays, implicit.py:216-219)
+        users_dev = _to_device_narrow(user_ids, device)
+        items_dev = _to_device_narrow(item_ids, device)
+        if users_dev.dtype != items_dev.dtype:
+            users_dev, items_dev = users_dev.long(), items_dev.long()
+        # _check_input (implicit.py:166-181) on the resident copy: same errors, no host pass
+        if len(user_ids):
+            self._check_input(int(users_dev.max()), int(items_dev.max()))
 
         for epoch_num in range(self._n_iter):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
@@ -205,8 +215,7 @@ class ImplicitFactorizationModel(object):
             else:                               # short epochs: the host loop beats the launches
                 order = shuffled_order(n, self._random_state)
                 order_dev = torch.from_numpy(order).to(device).long()
-            user_ids_tensor = users_dev.index_select(0, order_dev)
-            item_ids_tensor = items_dev.index_select(0, order_dev)
+            user_ids_tensor, item_ids_tensor = permute_ids(order_dev, users_dev, items_dev)
             del order_dev
 
             if route == 'epoch':

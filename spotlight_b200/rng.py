@@ -169,7 +169,7 @@ _SHUFFLE_WS = {}
 SHUFFLE_DEVICE_MAX = 1 << 29
 
 
-def shuffled_order_device(n, random_state, device, rounds=24):
+def shuffled_order_device(n, random_state, device, rounds=40):
     """``random_state.shuffle(arange(n))`` as an int64 CUDA tensor, computed on the device.
 
     Bit-exact with NumPy (same permutation, ``random_state`` left in the same state):
@@ -233,3 +233,23 @@ def shuffled_order_device(n, random_state, device, rounds=24):
     key = blocks[blk * _N:(blk + 1) * _N].cpu().numpy().view(np.uint32).copy()
     random_state.set_state(('MT19937', key, pos, st[3], st[4]))
     return order
+
+
+def permute_ids(order, users, items=None):
+    """``(users[order], items[order])`` as int64 CUDA tensors in one pass (the gathers of
+    spotlight/torch_utils.py:49-52); ``users`` / ``items`` are int32 or int64 CUDA tensors."""
+    lib = _lib.load()
+    n = order.numel()
+    if order.dtype != torch.int64 or not order.is_cuda:
+        raise ValueError('permute_ids: order must be an int64 CUDA tensor')
+    srcs = [users] if items is None else [users, items]
+    if any(t.dtype != users.dtype or t.numel() != n or not t.is_cuda for t in srcs) or \
+            users.dtype not in (torch.int32, torch.int64):
+        raise ValueError('permute_ids: ids must be CUDA int32/int64 tensors as long as order')
+    srcs = [t.contiguous() for t in srcs]
+    outs = [torch.empty(n, dtype=torch.int64, device=order.device) for _ in srcs]
+    rc = lib.slb_permute_ids(_ptr(order.contiguous()), n, _ptr(srcs[0]), _ptr(srcs[1]) if items is not None else None,
+                             users.element_size(), _ptr(outs[0]), _ptr(outs[1]) if items is not None else None,
+                             _stream())
+    _lib.check(rc, 'permute_ids')
+    return (outs[0], outs[1]) if items is not None else outs[0]

@@ -64,3 +64,30 @@ def test_fit_uses_device_shuffle_and_matches_host_path(monkeypatch):
         return m._net.item_embeddings.weight.detach().cpu().numpy().copy()
 
     assert np.array_equal(run(1), run(1 << 62))
+
+
+@pytest.mark.parametrize('dtype', [np.int32, np.int64])
+def test_permute_ids(dtype):
+    from spotlight_b200.rng import permute_ids
+    rs = np.random.RandomState(0)
+    n = 100003
+    u, it = rs.randint(0, 10 ** 6, n).astype(dtype), rs.randint(0, 10 ** 5, n).astype(dtype)
+    order = rs.permutation(n)
+    gu, gi = permute_ids(torch.from_numpy(order).cuda(), torch.from_numpy(u).cuda(), torch.from_numpy(it).cuda())
+    assert gu.dtype == torch.int64
+    assert np.array_equal(gu.cpu().numpy(), u[order]) and np.array_equal(gi.cpu().numpy(), it[order])
+    only = permute_ids(torch.from_numpy(order).cuda(), torch.from_numpy(u).cuda())
+    assert np.array_equal(only.cpu().numpy(), u[order])
+
+
+def test_fit_rejects_out_of_range_ids():
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    from spotlight_b200.interactions import Interactions
+    inter = Interactions(np.array([0, 1, 2], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32),
+                         num_users=3, num_items=3)
+    m = ImplicitFactorizationModel(n_iter=1, use_cuda=True, embedding_dim=8)
+    m.fit(inter)
+    bad = Interactions(np.array([0, 1, 5], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32),
+                       num_users=6, num_items=3)
+    with pytest.raises(ValueError, match='Maximum user id'):
+        m.fit(bad)
