@@ -16,7 +16,9 @@ a = bench.parse()
 model = bench.build_model(a, 0)
 dev = torch.device('cuda:0'); n = a.batch * a.steps
 rs = np.random.RandomState(7)
-hu = rs.randint(0, a.users, n).astype(np.int32); hi = rs.randint(0, a.items, n).astype(np.int32)
+pu = torch.empty(n, dtype=torch.int32).pin_memory(); pi = torch.empty(n, dtype=torch.int32).pin_memory()
+hu, hi = pu.numpy(), pi.numpy(); hu[:] = rs.randint(0, a.users, n); hi[:] = rs.randint(0, a.items, n)
+print('from_numpy(view of pinned).is_pinned():', torch.from_numpy(hu).is_pinned())
 
 def timed(name, fn, reps=2):
     for r in range(reps):

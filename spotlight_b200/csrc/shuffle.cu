@@ -283,8 +283,8 @@ scan_apply_kernel(const int32_t* __restrict__ x, int64_t n, const int32_t* __res
     for (int w = 0; w < warp; ++w) pre += sh[w];
 #pragma unroll
     for (int r = 0; r < SC_ITEMS; ++r) {
-        if (first + r < n) off[first + r] = pre;
         pre += c[r];
+        if (first + r < n) off[first + r] = pre;         // inclusive: one past the segment's last slot
     }
 }
 
@@ -300,15 +300,13 @@ __global__ void shuf_hist_kernel(const int32_t* __restrict__ jv, int32_t n, int3
         atomicAdd(cnt + jv[i], 1);
 }
 
-__global__ void shuf_fill_kernel(const int32_t* __restrict__ jv, int32_t n, int32_t* cnt,
-                                 const int32_t* __restrict__ off, int32_t* members, const int32_t* flags) {
+// cur[v] enters as the end offset of v's segment and leaves as its start offset.
+__global__ void shuf_fill_kernel(const int32_t* __restrict__ jv, int32_t n, int32_t* cur,
+                                 int32_t* members, const int32_t* flags) {
     if (!shuf_ok(flags, n)) return;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int32_t v = jv[i];
-        const int32_t old = atomicSub(cnt + v, 1);
-        members[off[v] + old - 1] = static_cast<int32_t>(i);
-    }
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        members[atomicSub(cur + jv[i], 1) - 1] = static_cast<int32_t>(i);
 }
 
 // Per target position v: sort its steps ascending, link each to the next one (parent),
@@ -456,7 +454,7 @@ int slb_shuffle_order(const uint32_t* blocks, int64_t nwords, int64_t* cursor, i
     scan_tilesum_kernel<<<l.nscan, SC_THREADS, 0, st>>>(l.cnt, n + 1, l.tsum);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(l.tsum, l.nscan);
     scan_apply_kernel<<<l.nscan, SC_THREADS, 0, st>>>(l.cnt, n + 1, l.tsum, l.off);
-    shuf_fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(l.jv, n32, l.cnt, l.off, l.members, l.flags);
+    shuf_fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(l.jv, n32, l.off, l.members, l.flags);
     shuf_link_kernel<<<grid_for(n, 256), 256, 0, st>>>(n32, l.off, l.members, l.parent, l.mlink, l.flags);
     shuf_final_kernel<<<grid_for(n, 256), 256, 0, st>>>(n32, l.jv, l.parent, l.mlink, order, l.flags);
     SLB_LAUNCH_CHECK("shuffle stage B");

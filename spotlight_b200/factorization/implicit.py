@@ -32,7 +32,8 @@ from spotlight_b200.factorization._components import _predict_process_ids
 from spotlight_b200.factorization.representations import BilinearNet
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
-from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, permute_ids, shuffled_order_device
+from spotlight_b200.rng import (SHUFFLE_DEVICE_MAX, permute_ids, shuffle_begin, shuffle_end,
+                                shuffled_order_device)
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
 
@@ -58,7 +59,8 @@ def _to_device_narrow(ids, device):
     arr = np.ascontiguousarray(ids)
     if arr.dtype not in (np.int32, np.int64):
         arr = arr.astype(np.int64)
-    return torch.from_numpy(arr).to(device)
+    host = torch.from_numpy(arr)
+    return host.to(device, non_blocking=host.is_pinned())     # page-locked callers get an async DMA
 
 
 # epochs at least this long take their permutation from the device shuffle (csrc/shuffle.cu);
@@ -195,22 +197,32 @@ class ImplicitFactorizationModel(object):
 
         route = self._route()
         device = self._device()
+        n = len(user_ids)
+        on_device = DEVICE_SHUFFLE_MIN <= n <= SHUFFLE_DEVICE_MAX and \
+            self._random_state.get_state()[0] == 'MT19937'
+        # the first epoch's permutation is resolved on the device while the ids travel
+        pending = shuffle_begin(n, self._random_state, device) if on_device and self._n_iter > 0 else None
         # ids go to the device once per fit(); each epoch only the permutation is made
         # there (the reference re-uploads both shuffled id arrays, implicit.py:216-219)
-        users_dev = _to_device_narrow(user_ids, device)
-        items_dev = _to_device_narrow(item_ids, device)
+        copy_stream = _side_stream(device)          # independent of the shuffle kernels just queued
+        with torch.cuda.stream(copy_stream):
+            users_dev = _to_device_narrow(user_ids, device)
+            items_dev = _to_device_narrow(item_ids, device)
+        torch.cuda.current_stream(device).wait_stream(copy_stream)
+        users_dev.record_stream(torch.cuda.current_stream(device))
+        items_dev.record_stream(torch.cuda.current_stream(device))
         if users_dev.dtype != items_dev.dtype:
             users_dev, items_dev = users_dev.long(), items_dev.long()
         # _check_input (implicit.py:166-181) on the resident copy: same errors, no host pass
-        if len(user_ids):
+        if n:
             self._check_input(int(users_dev.max()), int(items_dev.max()))
 
         for epoch_num in range(self._n_iter):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
             # (torch_utils.py:46-47); the fancy-index gathers run on the device
-            n = len(user_ids)
-            if DEVICE_SHUFFLE_MIN <= n <= SHUFFLE_DEVICE_MAX and \
-                    self._random_state.get_state()[0] == 'MT19937':
+            if pending is not None:
+                order_dev, pending = shuffle_end(pending), None
+            elif on_device:
                 order_dev = shuffled_order_device(n, self._random_state, device)
             else:                               # short epochs: the host loop beats the launches
                 order = shuffled_order(n, self._random_state)

@@ -178,10 +178,17 @@ def shuffled_order_device(n, random_state, device, rounds=40):
     parallel (csrc/shuffle.cu).  Replaces spotlight/torch_utils.py:46-47 for the epoch
     shuffle of factorization/implicit.py:212-214.
     """
+    return shuffle_end(shuffle_begin(n, random_state, device, rounds))
+
+
+def shuffle_begin(n, random_state, device, rounds=40, margin=8.0):
+    """Launches the device shuffle (asynchronous) and returns a handle for
+    :func:`shuffle_end`; ``random_state`` is only read here."""
     n = int(n)
     dev = torch.device(device)
+    h = dict(n=n, dev=dev, rs=random_state, rounds=int(rounds), margin=float(margin))
     if n <= 1:
-        return torch.zeros(n, dtype=torch.int64, device=dev)
+        return h
     if n > SHUFFLE_DEVICE_MAX:
         raise ValueError('shuffled_order_device: n must be <= 2**29')
     lib = _lib.load()
@@ -190,49 +197,63 @@ def shuffled_order_device(n, random_state, device, rounds=40):
         raise ValueError('shuffled_order_device needs a legacy MT19937 RandomState')
     key = np.ascontiguousarray(st[1], dtype=np.uint32)
     pos = int(st[2])
+    need_words = _shuffle_expected_words(n) + margin * math.sqrt(2.0 * n) + 64
+    nblocks = int(math.ceil((pos + need_words) / _N)) + 1
+    nwords = nblocks * _N
+    ws_bytes = lib.slb_shuffle_workspace_bytes(n, nwords - pos)
+    blocks, _, _, pin_key, _ = _scratch(dev, nwords, 0)
+    skey = (dev.index if dev.index is not None else torch.cuda.current_device(),
+            torch.cuda.current_stream(dev).cuda_stream)
+    cur = _SHUFFLE_WS.get(skey)
+    if cur is None or cur[0].numel() < ws_bytes:
+        cur = (torch.empty(ws_bytes + 4096, dtype=torch.uint8, device=dev),
+               torch.empty(4, dtype=torch.int64, device=dev))
+        _SHUFFLE_WS[skey] = cur
+    ws, cursor = cur
+    pin_key.copy_(torch.from_numpy(key.view(np.int32)))
+    blocks[:_N].copy_(pin_key, non_blocking=True)
+    if nblocks >= _PARALLEL_MIN_BLOCKS:
+        table, rows, states = _jump_table(dev)
+        _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
+                                                 _ptr(states), _stream()), 'mt19937_fill_parallel')
+    else:
+        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
     order = torch.empty(n, dtype=torch.int64, device=dev)
-    margin = 8.0
+    h.update(st=st, pos=pos, nwords=nwords, blocks=blocks, ws=ws, cursor=cursor, order=order)
+    _shuffle_launch(h, 0)
+    return h
+
+
+def _shuffle_launch(h, resume):
+    lib = _lib.load()
+    rc = lib.slb_shuffle_order(_ptr(h['blocks']), h['nwords'], _ptr(h['cursor']), h['pos'], h['n'],
+                               h['rounds'], resume, _ptr(h['order']), _ptr(h['ws']), h['ws'].numel(),
+                               _stream())
+    _lib.check(rc, 'shuffle_order')
+
+
+def shuffle_end(h):
+    """Waits for the permutation, hands the generator state back to ``random_state``."""
+    n = h['n']
+    if n <= 1:
+        return torch.zeros(n, dtype=torch.int64, device=h['dev'])
     while True:
-        need_words = _shuffle_expected_words(n) + margin * math.sqrt(2.0 * n) + 64
-        nblocks = int(math.ceil((pos + need_words) / _N)) + 1
-        nwords = nblocks * _N
-        ws_bytes = lib.slb_shuffle_workspace_bytes(n, nwords - pos)
-        blocks, _, _, pin_key, _ = _scratch(dev, nwords, 0)
-        skey = (dev.index if dev.index is not None else torch.cuda.current_device(),
-                torch.cuda.current_stream(dev).cuda_stream)
-        cur = _SHUFFLE_WS.get(skey)
-        if cur is None or cur[0].numel() < ws_bytes:
-            cur = (torch.empty(ws_bytes + 4096, dtype=torch.uint8, device=dev),
-                   torch.empty(4, dtype=torch.int64, device=dev))
-            _SHUFFLE_WS[skey] = cur
-        ws, cursor = cur
-        pin_key.copy_(torch.from_numpy(key.view(np.int32)))
-        blocks[:_N].copy_(pin_key, non_blocking=True)
-        if nblocks >= _PARALLEL_MIN_BLOCKS:
-            table, rows, states = _jump_table(dev)
-            _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
-                                                     _ptr(states), _stream()), 'mt19937_fill_parallel')
-        else:
-            _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
-        resume = 0
-        while True:
-            rc = lib.slb_shuffle_order(_ptr(blocks), nwords, _ptr(cursor), pos, n, int(rounds), resume,
-                                       _ptr(order), _ptr(ws), ws.numel(), _stream())
-            _lib.check(rc, 'shuffle_order')
-            end, swaps, converged, _ = (int(v) for v in cursor.tolist())     # the call's one sync
-            if converged:
-                break
-            resume = 1
+        end, swaps, converged, _ = (int(v) for v in h['cursor'].tolist())     # the call's one sync
+        if not converged:
+            _shuffle_launch(h, 1)               # more global rounds from the workspace's state
+            continue
         if swaps == n - 1:
             break
-        margin *= 4.0                       # stream too short (8-sigma event): regenerate longer
+        # stream too short (an 8-sigma event): regenerate a longer one
+        h = shuffle_begin(n, h['rs'], h['dev'], h['rounds'], h['margin'] * 4.0)
+    st, blocks = h['st'], h['blocks']
     if end % _N == 0 and end > 0:           # numpy leaves pos = 624 on a block boundary
         blk, pos = end // _N - 1, _N
     else:
         blk, pos = end // _N, end % _N
     key = blocks[blk * _N:(blk + 1) * _N].cpu().numpy().view(np.uint32).copy()
-    random_state.set_state(('MT19937', key, pos, st[3], st[4]))
-    return order
+    h['rs'].set_state(('MT19937', key, pos, st[3], st[4]))
+    return h['order']
 
 
 def permute_ids(order, users, items=None):
