@@ -305,6 +305,20 @@ __device__ __forceinline__ void cswap(int& x, int& y) {
     x = lo; y = hi;
 }
 
+// Sorted (5..CAP-term) segments: once the partner row ids are known (lane-parallel, after
+// the shared-memory sort) each lane asks L2 for its partners' rows, so the row walk that
+// follows -- GEN_CHUNK rows in flight per lane -- runs at L2 rather than HBM latency.
+// Measured at B = 524 288 (item rows average 10.5 terms): backward 301 -> 266 us.  The same
+// prefetch for a segment's own weight / state rows, and for short segments' partners, was
+// slower (+12 us), as were 16-row chunks and walking two user segments at once (spills).
+#ifndef GEN_CHUNK
+#define GEN_CHUNK 8
+#endif
+__device__ __forceinline__ void pf_row_l2(const float* row, int D) {
+    const char* p = reinterpret_cast<const char*>(row);
+    for (int o = 0; o < D * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 #ifndef BWD_MINB
 #define BWD_MINB 6
 #endif
@@ -407,7 +421,12 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                 }
                 __syncwarp(gmask);
                 const int32_t* pidx = sA ? t_b : t_a;
-                for (int i = gl; i < s_len; i += LPR) { pg[i] = t_g[srt[i]]; pp[i] = pidx[srt[i]]; }
+                for (int i = gl; i < s_len; i += LPR) {
+                    const int32_t pr = pidx[srt[i]];
+                    pg[i] = t_g[srt[i]];
+                    pp[i] = pr;
+                    if (!sA) pf_row_l2(ptab + static_cast<int64_t>(pr) * D, D);    // user rows: HBM; item rows sit in L2
+                }
                 __syncwarp(gmask);
                 n_gen = s_len;
             }
@@ -429,12 +448,12 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
                     const float* pg = reinterpret_cast<const float*>(sh + 2 * CAP);
                     const int32_t* pp = sh + 3 * CAP;
                     int i = 0;
-                    for (; i + 4 <= n_gen; i += 4) {
-                        float4 v[4];
+                    for (; i + GEN_CHUNK <= n_gen; i += GEN_CHUNK) {
+                        float4 v[GEN_CHUNK];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[k] = ldg4(ptab + static_cast<int64_t>(pp[i + k]) * D + c);
+                        for (int k = 0; k < GEN_CHUNK; ++k) v[k] = ldg4(ptab + static_cast<int64_t>(pp[i + k]) * D + c);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { fma4(acc, pg[i + k], v[k]); b2 += pg[i + k]; }
+                        for (int k = 0; k < GEN_CHUNK; ++k) { fma4(acc, pg[i + k], v[k]); b2 += pg[i + k]; }
                     }
                     for (; i < n_gen; ++i) {
                         fma4(acc, pg[i], ldg4(ptab + static_cast<int64_t>(pp[i]) * D + c));

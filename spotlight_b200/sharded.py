@@ -34,6 +34,7 @@ backend there; this module itself never imports the oracle).
 
 import ctypes
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -122,6 +123,29 @@ class GpuBackend(object):
         adagrad_dense_(st.bi, st.sbi, db.reshape(-1), st.lr, st.eps)
 
 
+    # ---- epoch-level pieces of fit() (all ranks compute the same global stream) ----
+    def to_device(self, ids):
+        arr = np.ascontiguousarray(ids)
+        if arr.dtype not in (np.int32, np.int64):
+            arr = arr.astype(np.int64)
+        host = torch.from_numpy(arr)
+        return host.to(self.device, non_blocking=host.is_pinned())
+
+    def shuffled_order(self, n, random_state):
+        from spotlight_b200 import rng
+        from spotlight_b200.torch_utils import shuffled_order
+        if n >= (1 << 17) and n <= rng.SHUFFLE_DEVICE_MAX:
+            return rng.shuffled_order_device(n, random_state, self.device)
+        return torch.from_numpy(shuffled_order(n, random_state)).to(self.device).long()
+
+    def permute(self, order, users, items):
+        from spotlight_b200 import rng
+        return rng.permute_ids(order, users, items)
+
+    def sample(self, num_items, count, random_state):
+        from spotlight_b200.sampling import sample_items
+        return sample_items(num_items, count, random_state=random_state, device=self.device)
+
     def seq_local_step(self, E_cache, bias_cache, n_cache, seqs_idx, negs_idx, loss, cnn, norm_count):
         """Fused sequence step on the row cache (ids already remapped onto it; cache
         row 0 is the padding row).  Returns (loss share, dE_cache, dbias_cache, dconv_w, dconv_b)."""
@@ -198,7 +222,8 @@ class ShardedMF(object):
             # *global* batch (implicit.py:270-275), i.e. with user rows other ranks own;
             # reproducing that needs a user-row exchange that is not built yet.
             raise NotImplementedError('sharded adaptive hinge is not supported yet')
-        if exchange == 'dense' or (exchange == 'auto' and self._dense_exchange_pays(users.numel())):
+        if exchange == 'dense' or (exchange == 'auto' and
+                                   self._dense_exchange_pays(global_batch // self.plan.world)):
             return self.step_dense(users, items, negs, loss, global_batch, n_neg)
         return self.step_a2a(users, items, negs, loss, global_batch, n_neg)
 
@@ -219,8 +244,11 @@ class ShardedMF(object):
         dist.all_gather_into_tensor(full_b, pad_b, group=self.group)
         self.stats['bytes_a2a'] += (full_W.numel() + full_b.numel()) * 4
         self.stats['rows_requested'] += P * chunk
-        loss_share, g_rows, g_bias = self.backend.local_step(
-            st, full_W, full_b, P * chunk, users - st.ulo, items, negs, loss, global_batch, n_neg)
+        if users.numel():
+            loss_share, g_rows, g_bias = self.backend.local_step(
+                st, full_W, full_b, P * chunk, users - st.ulo, items, negs, loss, global_batch, n_neg)
+        else:                               # none of this minibatch's users live here
+            loss_share, g_rows, g_bias = full_b.new_zeros(()), torch.zeros_like(full_W), torch.zeros_like(full_b)
         g_shard = self._reduce_scatter(g_rows.contiguous(), chunk)
         gb_shard = self._reduce_scatter(g_bias.contiguous(), chunk)
         self.stats['bytes_a2a'] += (g_rows.numel() + g_bias.numel()) * 4
@@ -252,7 +280,10 @@ class ShardedMF(object):
         dev = users.device
         # 1. bucket the distinct item ids by owner
         ids = torch.cat([items, negs])
-        uniq, inverse, bounds = self.backend.unique_bucket(ids, plan.num_items, plan.ichunk, P)
+        if B:
+            uniq, inverse, bounds = self.backend.unique_bucket(ids, plan.num_items, plan.ichunk, P)
+        else:                               # none of this minibatch's users live here: serve peers only
+            uniq, inverse, bounds = ids, ids, [0] * (P + 1)
         send_counts = [bounds[p + 1] - bounds[p] for p in range(P)]
         # 2. exchange the request sizes, then the requests
         sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
@@ -276,9 +307,12 @@ class ShardedMF(object):
             cache_rows, cache_bias = full, fb
         self.stats['rows_requested'] += n_cache
         # 4. fused local step (user rows updated in place)
-        loss_share, g_rows, g_bias = self.backend.local_step(
-            st, cache_rows, cache_bias, n_cache, users - st.ulo, inverse[:B], inverse[B:], loss,
-            global_batch, n_neg)
+        if B:
+            loss_share, g_rows, g_bias = self.backend.local_step(
+                st, cache_rows, cache_bias, n_cache, users - st.ulo, inverse[:B], inverse[B:], loss,
+                global_batch, n_neg)
+        else:
+            loss_share, g_rows, g_bias = st.bi.new_zeros(()), cache_rows[:0], cache_bias[:0]
         # 5. item gradients go home; owners reduce in rank order and update their shard
         g_recv = self._a2a(g_rows, send_counts, recv_counts)
         gb_recv = self._a2a(g_bias, send_counts, recv_counts)
@@ -380,3 +414,77 @@ class ShardedSeq(object):
         total = loss_share.detach().clone().reshape(1)
         dist.all_reduce(total, group=self.group)
         return total.reshape(())
+
+
+class ShardedImplicitFactorizationModel(object):
+    """``ImplicitFactorizationModel.fit`` on N GPUs (one process per GPU), with the
+    *single-process* semantics of the reference loop (factorization/implicit.py:184-252):
+
+    * one global ``RandomState`` stream, advanced identically on every rank: the epoch
+      permutation (``shuffle``) and the negatives (``sample_items`` once per minibatch) are
+      the reference's, bit for bit;
+    * minibatch k is ``shuffled[k*B:(k+1)*B]`` of the *global* data set; each rank trains
+      the members whose user it owns and the loss / gradients are those of the whole
+      minibatch (:class:`ShardedMF`);
+    * ``epoch_loss`` is the mean of the global minibatch losses.
+
+    Every rank is handed the same ``Interactions`` (the global shuffle needs all of it);
+    parameters and optimizer state are sharded, never replicated.  Optimizer: row-wise
+    Adagrad (``spotlight_b200.optim.fused_adagrad``'s update).  Losses: bpr, hinge,
+    pointwise.
+    """
+
+    def __init__(self, num_users, num_items, rank, world, device, backend=None, loss='bpr',
+                 embedding_dim=32, n_iter=10, batch_size=256, learning_rate=0.05, random_state=None,
+                 exchange='auto', init=None, group=None):
+        assert loss in ('pointwise', 'bpr', 'hinge')
+        self._loss, self._n_iter, self._batch_size = loss, int(n_iter), int(batch_size)
+        self._num_users, self._num_items = int(num_users), int(num_items)
+        self._random_state = random_state or np.random.RandomState()
+        self._exchange = exchange
+        self.rank, self.world = rank, world
+        self.plan = ShardPlan(num_users, num_items, world)
+        self.backend = backend or GpuBackend(device)
+        # the reference seeds torch from the model stream at construction (implicit.py:114);
+        # the draw is kept so that the stream position matches the single-process model
+        seed = int(self._random_state.randint(-10 ** 8, 10 ** 8))
+        if init is None:
+            torch.manual_seed(seed + 7919 * rank)
+        self.state = ShardState(self.plan, rank, embedding_dim, device, lr=learning_rate, init=init)
+        self.mf = ShardedMF(self.plan, self.state, rank, self.backend, group=group)
+        self.epoch_losses = []
+
+    def fit(self, interactions, verbose=False):
+        plan, be, B = self.plan, self.backend, self._batch_size
+        n = len(interactions.user_ids)
+        users_dev = be.to_device(interactions.user_ids)
+        items_dev = be.to_device(interactions.item_ids)
+        if users_dev.dtype != items_dev.dtype:
+            users_dev, items_dev = users_dev.long(), items_dev.long()
+        if n and int(users_dev.max()) >= self._num_users:
+            raise ValueError('Maximum user id greater than number of users in model.')
+        if n and int(items_dev.max()) >= self._num_items:
+            raise ValueError('Maximum item id greater than number of items in model.')
+        for epoch in range(self._n_iter):
+            order = be.shuffled_order(n, self._random_state)
+            u, i = be.permute(order, users_dev, items_dev)
+            del order
+            negs = be.sample(self._num_items, n, self._random_state)
+            # this rank's members of every minibatch, in minibatch order
+            mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
+            edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
+            bounds = torch.searchsorted(mine, edges).tolist()
+            mu, mi, mn = u[mine], i[mine], negs[mine]
+            del u, i, negs, mine
+            losses = []
+            for k in range(len(bounds) - 1):
+                sl = slice(bounds[k], bounds[k + 1])
+                losses.append(self.mf.step(mu[sl], mi[sl], mn[sl], self._loss, min(B, n - k * B),
+                                           self._exchange))
+            epoch_loss = float(torch.stack(losses).mean()) if losses else 0.0
+            self.epoch_losses.append(epoch_loss)
+            if verbose and self.rank == 0:
+                print('Epoch {}: loss {}'.format(epoch, epoch_loss))
+            if np.isnan(epoch_loss) or epoch_loss == 0.0:
+                raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
+        return self

@@ -39,6 +39,21 @@ class NumpyBackend(object):
                 torch.from_numpy((r['dWi'] * scale).astype(np.float32))[:n_cache],
                 torch.from_numpy((r['dbi'].reshape(-1) * scale).astype(np.float32))[:n_cache])
 
+    # epoch-level pieces of the sharded fit(), host NumPy (the reference's own calls)
+    def to_device(self, ids):
+        return torch.from_numpy(np.ascontiguousarray(ids).astype(np.int64))
+
+    def shuffled_order(self, n, random_state):
+        order = np.arange(n)
+        random_state.shuffle(order)
+        return torch.from_numpy(order)
+
+    def permute(self, order, users, items):
+        return users[order], items[order]
+
+    def sample(self, num_items, count, random_state):
+        return torch.from_numpy(random_state.randint(0, num_items, count, dtype=np.int64))
+
     def seq_local_step(self, E_cache, bias_cache, n_cache, seqs_idx, negs_idx, loss, cnn, norm_count):
         E = E_cache.numpy().astype(np.float64)
         b = bias_cache.numpy().astype(np.float64).reshape(-1, 1)
@@ -181,3 +196,47 @@ def seq_sharded_run(rank, world, params, batches, loss, lr, device, backend, cnn
         out.append(torch.cat(parts)[:I].cpu().numpy())
     out += [x.cpu().numpy() for wb in st.convs for x in wb]
     return out, losses, model.stats
+
+
+def reference_epochs(seed, users, items, num_items, B, n_iter):
+    """The minibatches the reference loop forms (factorization/implicit.py:114,212-259):
+    ctor draw, then per epoch shuffle + one randint per minibatch, all from one stream."""
+    rs = np.random.RandomState(seed)
+    rs.randint(-10 ** 8, 10 ** 8)
+    epochs = []
+    for _ in range(n_iter):
+        order = np.arange(len(users))
+        rs.shuffle(order)
+        u, i = users[order], items[order]
+        batches = []
+        for lo in range(0, len(u), B):
+            bu, bi = u[lo:lo + B].astype(np.int64), i[lo:lo + B].astype(np.int64)
+            batches.append((bu, bi, rs.randint(0, num_items, len(bu), dtype=np.int64)))
+        epochs.append(batches)
+    return epochs, rs
+
+
+def gather_tables(st, plan, U, I, world):
+    out = []
+    for shard, n, chunk in ((st.Wu, U, plan.uchunk), (st.Wi, I, plan.ichunk),
+                            (st.bu.reshape(-1, 1), U, plan.uchunk), (st.bi.reshape(-1, 1), I, plan.ichunk)):
+        pad = torch.zeros((chunk,) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        pad[:shard.shape[0]] = shard
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat(parts)[:n].cpu().numpy())
+    return out
+
+
+def sharded_fit_run(rank, world, params, users, items, loss, device, backend, seed, B, n_iter, exchange):
+    from spotlight_b200.interactions import Interactions
+    from spotlight_b200.sharded import ShardedImplicitFactorizationModel
+    U, D = params[0].shape
+    I = params[1].shape[0]
+    rs = np.random.RandomState(seed)
+    model = ShardedImplicitFactorizationModel(U, I, rank, world, device, backend=backend, loss=loss,
+                                              embedding_dim=D, n_iter=n_iter, batch_size=B,
+                                              learning_rate=0.05, random_state=rs, exchange=exchange,
+                                              init=[torch.from_numpy(p) for p in params])
+    model.fit(Interactions(users, items, num_users=U, num_items=I))
+    return gather_tables(model.state, model.plan, U, I, world), model.epoch_losses, rs.get_state()

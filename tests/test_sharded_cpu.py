@@ -110,6 +110,61 @@ def test_sharded_sequence_step_matches_single_process(world, loss, net):
     assert not got[0][0].any() and not got[1][0].any()          # padding row stays zero
 
 
+FIT = dict(seed=21, U=61, I=37, D=8, n=500, B=64, n_iter=2)
+
+
+def _fit_problem():
+    rs = np.random.RandomState(4)
+    params, _ = __import__('sharded_common').make_problem(5, FIT['U'], FIT['I'], FIT['D'], 8, 0)
+    users = rs.randint(0, 40, FIT['n']).astype(np.int32)          # world 3: rank 2 owns users >= 42, always empty
+    items = rs.randint(0, FIT['I'], FIT['n']).astype(np.int32)
+    return params, users, items
+
+
+def _fit_worker(rank, world, port, loss, exchange, q):
+    import sharded_common as sc
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        params, users, items = _fit_problem()
+        out = sc.sharded_fit_run(rank, world, params, users, items, loss, 'cpu', sc.NumpyBackend(),
+                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange)
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (3, 'pointwise', 'dense')])
+def test_sharded_fit_is_the_single_process_fit(world, loss, exchange):
+    """fit() on N ranks forms the reference's minibatches from the reference's RandomState
+    stream (global shuffle, one randint per minibatch), so its trajectory is the
+    single-process one; with 500 interactions in minibatches of 64 over 3 ranks some ranks
+    get empty shares, which must not stall the collectives."""
+    import sharded_common as sc
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() + world * 13) % 2000
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, loss, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses, state = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params, users, items = _fit_problem()
+    epochs, rs = sc.reference_epochs(FIT['seed'], users, items, FIT['I'], FIT['B'], FIT['n_iter'])
+    flat = [b for e in epochs for b in e]
+    ref, ref_losses = sc.oracle_run(params, flat, loss, 0.05)
+    per_epoch = np.array(ref_losses).reshape(FIT['n_iter'], -1).mean(axis=1)
+    assert_close(np.array(losses), per_epoch, 1e-5, what='epoch losses')
+    for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
+        assert_close(a, b, 5e-5, what=nm)
+    want = rs.get_state()
+    assert np.array_equal(state[1], want[1]) and state[2] == want[2]      # stream position too
+
+
 def test_shard_plan_ranges():
     from spotlight_b200.sharded import ShardPlan
     plan = ShardPlan(10, 7, 4)

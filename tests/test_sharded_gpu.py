@@ -110,3 +110,75 @@ def test_sharded_sequence_gpu_matches_oracle(loss, net):
     assert_close(np.array(losses), np.array(ref_losses), 2e-5, what='losses')
     for k, (a, b) in enumerate(zip(got, ref)):
         assert_close(a, b, 5e-3, what='param%d' % k)      # Adagrad trajectory tolerance, as above
+
+
+FIT = dict(seed=33, U=3000, I=800, D=32, n=300000, B=16384, n_iter=2)
+
+
+def _fit_problem():
+    import sharded_common as sc
+    rs = np.random.RandomState(8)
+    params, _ = sc.make_problem(6, FIT['U'], FIT['I'], FIT['D'], 8, 0)
+    params = tuple(p * 0.3 for p in params)
+    return params, rs.randint(0, FIT['U'], FIT['n']).astype(np.int32), rs.randint(0, FIT['I'], FIT['n']).astype(np.int32)
+
+
+def _fit_worker(rank, world, port, exchange, q):
+    import sharded_common as sc
+    from spotlight_b200.sharded import GpuBackend
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        params, users, items = _fit_problem()
+        dev = torch.device('cuda', rank)
+        out = sc.sharded_fit_run(rank, world, params, users, items, 'bpr', dev, GpuBackend(dev),
+                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange)
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('exchange', ['a2a', 'dense'])
+def test_sharded_fit_equals_single_gpu_fit(exchange):
+    """2-GPU fit() vs the single-GPU product fit() from the same RandomState seed and
+    weights: same permutation (device shuffle, n >= 2^17), same negatives, same minibatches
+    -> same epoch losses, same final tables, same final generator state."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    from spotlight_b200.interactions import Interactions
+    from spotlight_b200.optim import fused_adagrad
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() * 7) % 2000
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses, state = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params, users, items = _fit_problem()
+    inter = Interactions(users, items, num_users=FIT['U'], num_items=FIT['I'])
+    rs = np.random.RandomState(FIT['seed'])
+    one = ImplicitFactorizationModel(loss='bpr', embedding_dim=FIT['D'], n_iter=FIT['n_iter'],
+                                     batch_size=FIT['B'], use_cuda=True, random_state=rs,
+                                     optimizer_func=fused_adagrad(lr=0.05))
+    one._initialize(inter)
+    net = one._net
+    with torch.no_grad():
+        for prm, val in zip((net.user_embeddings.weight, net.item_embeddings.weight,
+                             net.user_biases.weight, net.item_biases.weight), params):
+            prm.copy_(torch.from_numpy(val).to(prm.device).reshape(prm.shape))
+    one.fit(inter, verbose=False)
+    ref = [p.detach().cpu().numpy() for p in (net.user_embeddings.weight, net.item_embeddings.weight,
+                                              net.user_biases.weight, net.item_biases.weight)]
+    for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
+        assert_close(a, b.reshape(a.shape), 5e-3, what=nm)       # Adagrad trajectory tolerance, as above
+    want = rs.get_state()
+    assert np.array_equal(state[1], want[1]) and state[2] == want[2]
+    assert len(losses) == FIT['n_iter'] and all(0.0 < v < 1.0 for v in losses)
