@@ -249,6 +249,45 @@ def kernel_breakdown(model, users, items, a, steps):
     return {nm: tot[nm] / steps for nm in names}
 
 
+def sharded_e2e(a, rank, world, dev):
+    """fit() through the public multi-GPU API on host ids; returns the e2e object."""
+    import torch
+    import torch.distributed as dist
+    from spotlight_b200.interactions import Interactions
+    from spotlight_b200.sharded import ShardedImplicitFactorizationModel
+    B, K = a.batch, a.steps
+    n_all = world * K * B                    # weak scaling: K global minibatches of world * B
+    rs = np.random.RandomState(7)            # every rank holds the same global data set
+    pin_u = torch.empty(n_all, dtype=torch.int32).pin_memory()
+    pin_i = torch.empty(n_all, dtype=torch.int32).pin_memory()
+    hu, hi = pin_u.numpy(), pin_i.numpy()
+    hu[:] = rs.randint(0, a.users, n_all)
+    hi[:] = rs.randint(0, a.items, n_all)
+    inter = Interactions(hu, hi, num_users=a.users, num_items=a.items)
+    fm = ShardedImplicitFactorizationModel(a.users, a.items, rank, world, dev, loss=a.loss,
+                                           embedding_dim=a.dim, n_iter=1, batch_size=world * B,
+                                           learning_rate=a.lr, random_state=np.random.RandomState(5),
+                                           exchange=a.exchange)
+    calls = []
+    for _ in range(2):                       # first call warms the allocator (reported too)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fm.fit(inter)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        calls.append(n_all / float(t.item()))
+    e2e = {'value': calls[1], 'unit': UNIT, 'first_call_value': calls[0],
+           'h2d_bytes_per_step': 8 * world * B, 'd2h_bytes_per_step': 4,
+           'note': 'ShardedImplicitFactorizationModel.fit(Interactions) on every rank with the same '
+                   'page-locked host int32 ids: H2D, range check, the global bit-exact '
+                   'RandomState.shuffle permutation and the global negative stream computed on every '
+                   'rank (single-process minibatch membership), owner routing, K sharded steps of '
+                   'global batch world*B, loss read-back; wall clock, max over ranks, second of two calls'}
+    return e2e
+
+
 def main_sharded(a, rank, world, local):
     """N > 1: item rows range-sharded over the ranks, users owner-routed, NCCL
     all-to-all of requests / rows / gradient rows (spotlight_b200/sharded.py).
@@ -299,40 +338,14 @@ def main_sharded(a, rank, world, local):
 
     # ---- end to end through the public multi-GPU API (host ids) ---------
     e2e = None
+    stats = dict(model.stats)
     if not a.no_e2e:
-        from spotlight_b200.interactions import Interactions
-        from spotlight_b200.sharded import ShardedImplicitFactorizationModel
         del users, items, negs, model, st
         torch.cuda.empty_cache()
-        n_all = world * K * B                    # weak scaling: K global minibatches of world * B
-        rs = np.random.RandomState(7)            # every rank holds the same global data set
-        pin_u = torch.empty(n_all, dtype=torch.int32).pin_memory()
-        pin_i = torch.empty(n_all, dtype=torch.int32).pin_memory()
-        hu, hi = pin_u.numpy(), pin_i.numpy()
-        hu[:] = rs.randint(0, a.users, n_all)
-        hi[:] = rs.randint(0, a.items, n_all)
-        inter = Interactions(hu, hi, num_users=a.users, num_items=a.items)
-        fm = ShardedImplicitFactorizationModel(a.users, a.items, rank, world, dev, loss=a.loss,
-                                               embedding_dim=a.dim, n_iter=1, batch_size=world * B,
-                                               learning_rate=a.lr, random_state=np.random.RandomState(5),
-                                               exchange=a.exchange)
-        calls = []
-        for _ in range(2):                       # first call warms the allocator (reported too)
-            dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fm.fit(inter)
-            torch.cuda.synchronize()
-            t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            calls.append(n_all / float(t.item()))
-        e2e = {'value': calls[1], 'unit': UNIT, 'first_call_value': calls[0],
-               'h2d_bytes_per_step': 8 * world * B, 'd2h_bytes_per_step': 4,
-               'note': 'ShardedImplicitFactorizationModel.fit(Interactions) on every rank with the same '
-                       'page-locked host int32 ids: H2D, range check, the global bit-exact '
-                       'RandomState.shuffle permutation and the global negative stream computed on every '
-                       'rank (single-process minibatch membership), owner routing, K sharded steps of '
-                       'global batch world*B, loss read-back; wall clock, max over ranks, second of two calls'}
+        try:
+            e2e = sharded_e2e(a, rank, world, dev)
+        except Exception as exc:                 # keep the device-timed line even if the e2e leg fails
+            e2e = {'value': None, 'unit': UNIT, 'error': repr(exc)[:300]}
 
     if rank == 0:
         cfg = workload_config(a, world)
@@ -342,7 +355,7 @@ def main_sharded(a, rank, world, local):
                                          'num_items: every row is needed by every rank)' if dense else
                                          'NCCL all-to-all of requests / rows / gradient rows'))
         cfg['negatives'] = 'device MT19937 per rank (seeded per rank), pre-drawn'
-        a2a_gb = model.stats['bytes_a2a'] / 1e9
+        a2a_gb = stats['bytes_a2a'] / 1e9
         line = {'metric': METRIC, 'value': world * K * B / (ms * 1e-3), 'unit': UNIT,
                 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -350,7 +363,7 @@ def main_sharded(a, rank, world, local):
                 'e2e': e2e, 'gpu_launches': K * 30,
                 'nvlink': {'all_to_all_gbytes_per_rank': a2a_gb,
                            'achieved_gbs_per_rank': a2a_gb / (ms * 1e-3),
-                           'rows_requested_per_step': model.stats['rows_requested'] / K},
+                           'rows_requested_per_step': stats['rows_requested'] / K},
                 'roofline': None, 'cpu_baseline': None}
         print(json.dumps(line))
     dist.destroy_process_group()
