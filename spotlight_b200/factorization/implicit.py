@@ -201,7 +201,9 @@ class ImplicitFactorizationModel(object):
         on_device = DEVICE_SHUFFLE_MIN <= n <= SHUFFLE_DEVICE_MAX and \
             self._random_state.get_state()[0] == 'MT19937'
         # the first epoch's permutation is resolved on the device while the ids travel
-        pending = shuffle_begin(n, self._random_state, device) if on_device and self._n_iter > 0 else None
+        main = torch.cuda.current_stream(device)
+        pending = (shuffle_begin(n, self._random_state, device), main) if on_device and self._n_iter > 0 \
+            else None
         # ids go to the device once per fit(); each epoch only the permutation is made
         # there (the reference re-uploads both shuffled id arrays, implicit.py:216-219)
         copy_stream = _side_stream(device)          # independent of the shuffle kernels just queued
@@ -221,7 +223,13 @@ class ImplicitFactorizationModel(object):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
             # (torch_utils.py:46-47); the fancy-index gathers run on the device
             if pending is not None:
-                order_dev, pending = shuffle_end(pending), None
+                handle, stream = pending
+                with torch.cuda.stream(stream):           # any extra rounds go where it was begun
+                    order_dev = shuffle_end(handle)
+                if stream is not main:
+                    main.wait_stream(stream)
+                    order_dev.record_stream(main)
+                pending = None
             elif on_device:
                 order_dev = shuffled_order_device(n, self._random_state, device)
             else:                               # short epochs: the host loop beats the launches
@@ -231,7 +239,16 @@ class ImplicitFactorizationModel(object):
             del order_dev
 
             if route == 'epoch':
-                epoch_loss = self._run_epoch_device(user_ids_tensor, item_ids_tensor)
+                def next_permutation(last=epoch_num + 1 >= self._n_iter):
+                    # the epoch's last negatives are drawn: the stream now stands where the next
+                    # shuffle starts, and that shuffle can run under this epoch's remaining steps
+                    nonlocal pending
+                    if on_device and not last:
+                        side = _side_stream(device)
+                        with torch.cuda.stream(side):
+                            pending = (shuffle_begin(n, self._random_state, device), side)
+                epoch_loss = self._run_epoch_device(user_ids_tensor, item_ids_tensor,
+                                                    after_sampling=next_permutation)
             else:
                 negatives = self._epoch_negatives(len(user_ids))
                 epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
@@ -243,7 +260,7 @@ class ImplicitFactorizationModel(object):
             if np.isnan(epoch_loss) or epoch_loss == 0.0:
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
 
-    def _run_epoch_device(self, users, items, chunk_batches=64):
+    def _run_epoch_device(self, users, items, chunk_batches=64, after_sampling=None):
         """The epoch pipeline over device-resident (already shuffled) ids.
 
         Negatives are drawn chunk by chunk on a side stream (the MT19937 block
@@ -274,6 +291,8 @@ class ImplicitFactorizationModel(object):
                                     device=dev, out=negs_all[lo_v:drawn[0]])
                 ev = torch.cuda.Event()
                 ev.record(side)
+            if after_sampling is not None and drawn[0] == n * n_neg:
+                after_sampling()                # RandomState is final for this epoch
             return negs, ev
 
         keep, parts = [], []
