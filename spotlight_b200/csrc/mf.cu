@@ -200,7 +200,11 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
+#ifdef D_CT
+    constexpr int D = D_CT;
+#else
     const int D = a.D;
+#endif
     const float invB = 1.0f / static_cast<float>(a.NB);
     const int64_t ntiles = (a.B + TI - 1) / TI;
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
@@ -322,11 +326,14 @@ __device__ __forceinline__ void pf_row_l2(const float* row, int D) {
 #ifndef BWD_MINB
 #define BWD_MINB 6
 #endif
+#ifndef BWD_MINB1
+#define BWD_MINB1 BWD_MINB
+#endif
 #ifndef BWD_FAST
 #define BWD_FAST 4
 #endif
 template <int LPR, int MODE, int TI>
-__global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(MfDev a) {
+__global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_MINB) mf_bwd_tile_kernel(MfDev a) {
     constexpr int GPW = 32 / LPR;
     constexpr int ITERS = TI / GPW > 0 ? TI / GPW : 1;
     constexpr int WARPS = MF_TILE_THREADS / 32;
@@ -337,7 +344,11 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, BWD_MINB) mf_bwd_tile_kernel(
     const int grp = lane / LPR;
     const unsigned gmask = group_mask(LPR);
     int32_t* sh = sh_all + ((threadIdx.x >> 5) * GPW + grp) * 4 * CAP;
+#ifdef D_CT
+    constexpr int D = D_CT;
+#else
     const int D = a.D;
+#endif
     const int nseg = a.seg.totals[0];
     const int nsegA = a.seg.totals[2];
     if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {

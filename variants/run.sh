@@ -1,6 +1,6 @@
 #!/bin/bash
 # kernel breakdown of one step for each variant library
-for lib in refac g8 g8p6 g8p5 g8p4 g16p5; do
+for lib in base dct m15 m14 dctm15 dctm7; do
   if [ $lib = base ]; then unset SLB_LIBRARY; else export SLB_LIBRARY=/root/repo/variants/lib_$lib.so; fi
   timeout 200 python bench.py --no-cpu-baseline --no-e2e --steps 100 --warmup 10 2>/dev/null | python -c "
 import sys, json
