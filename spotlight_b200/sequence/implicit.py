@@ -19,10 +19,13 @@ import torch.optim as optim
 from spotlight_b200 import ops
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
+from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, shuffled_order_device
 from spotlight_b200.sampling import sample_items
 from spotlight_b200.sequence.representations import (PADDING_IDX, CNNNet, LSTMNet,
                                                      MixtureLSTMNet, PoolNet)
 from spotlight_b200.torch_utils import cpu, gpu, minibatch, set_seed, shuffled_order
+
+DEVICE_SHUFFLE_MIN = 1 << 17        # as factorization/implicit.py: a speed knob, both paths are bit-exact
 
 _NO_CPU = ('spotlight_b200 runs the fit() hot path in sm_100a CUDA kernels and has no CPU '
            'route; construct the model with use_cuda=True.')
@@ -122,13 +125,24 @@ class ImplicitSequenceModel(object):
         n_neg = self._n_neg()
         device = next(self._net.parameters()).device
 
+        # the sequences go to the device once per fit(); every epoch permutes the resident rows
+        # (cumulatively, as the reference's `sequences = sequences[shuffle_indices]` does,
+        # implicit.py:217-220) instead of re-indexing on the host and re-uploading
+        sequences_tensor = gpu(torch.from_numpy(np.ascontiguousarray(sequences)), self._use_cuda)
+        n_seq = len(sequences)
+
         for epoch_num in range(self._n_iter):
-            sequences = sequences[shuffled_order(len(sequences), self._random_state)]
-            sequences_tensor = gpu(torch.from_numpy(sequences), self._use_cuda)
+            if DEVICE_SHUFFLE_MIN <= n_seq <= SHUFFLE_DEVICE_MAX and \
+                    self._random_state.get_state()[0] == 'MT19937':
+                order = shuffled_order_device(n_seq, self._random_state, device)
+            else:
+                order = torch.from_numpy(shuffled_order(n_seq, self._random_state)).to(device).long()
+            sequences_tensor = sequences_tensor.index_select(0, order)
+            del order
             S = sequences_tensor.shape[1]
             # Per-minibatch draws of shape (n*B, S) (implicit.py:268-271, 283-285)
             # concatenate to one stream-equivalent draw over the epoch.
-            negatives = sample_items(self._num_items, (len(sequences) * n_neg, S),
+            negatives = sample_items(self._num_items, (n_seq * n_neg, S),
                                      random_state=self._random_state, device=device)
 
             epoch_loss = torch.zeros((), dtype=torch.float64, device=device)
