@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_kernel(MfDev a) {
 // ---------------------------------------------------------------------------
 constexpr int MF_TILE_THREADS = 128;
 
-template <int LPR, int LOSS, int TI>
+template <int LPR, int LOSS, int TI, bool EX>
 __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     __shared__ float sh_red[MF_TILE_THREADS / 32];
     __shared__ bool is_last;
@@ -200,11 +200,9 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
-#ifdef D_CT
-    constexpr int D = D_CT;
-#else
-    const int D = a.D;
-#endif
+    // EX: the row is exactly one 128-bit load per lane (D == 4 * LPR), so D is a compile-time
+    // constant: no column loop, shifts for the row offsets (B200, D = 64: step 476 -> 431 us)
+    const int D = EX ? LPR * 4 : a.D;
     const float invB = 1.0f / static_cast<float>(a.NB);
     const int64_t ntiles = (a.B + TI - 1) / TI;
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (MF_TILE_THREADS / 32);
@@ -332,7 +330,7 @@ __device__ __forceinline__ void pf_row_l2(const float* row, int D) {
 #ifndef BWD_FAST
 #define BWD_FAST 4
 #endif
-template <int LPR, int MODE, int TI>
+template <int LPR, int MODE, int TI, bool EX>
 __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_MINB) mf_bwd_tile_kernel(MfDev a) {
     constexpr int GPW = 32 / LPR;
     constexpr int ITERS = TI / GPW > 0 ? TI / GPW : 1;
@@ -344,11 +342,9 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
     const int grp = lane / LPR;
     const unsigned gmask = group_mask(LPR);
     int32_t* sh = sh_all + ((threadIdx.x >> 5) * GPW + grp) * 4 * CAP;
-#ifdef D_CT
-    constexpr int D = D_CT;
-#else
-    const int D = a.D;
-#endif
+    // EX: the row is exactly one 128-bit load per lane (D == 4 * LPR), so D is a compile-time
+    // constant: no column loop, shifts for the row offsets (B200, D = 64: step 476 -> 431 us)
+    const int D = EX ? LPR * 4 : a.D;
     const int nseg = a.seg.totals[0];
     const int nsegA = a.seg.totals[2];
     if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
@@ -907,14 +903,17 @@ int lpr_for_dim(int D) {
         default: KERNEL<32, P2><<<grid, block, 0, stream>>>(__VA_ARGS__); break;             \
     }
 
-#define DISPATCH_LPR3(lpr, KERNEL, P2, P3, grid, block, stream, ...)                           \
-    switch (lpr) {                                                                           \
-        case 1: KERNEL<1, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
-        case 2: KERNEL<2, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
-        case 4: KERNEL<4, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
-        case 8: KERNEL<8, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;           \
-        case 16: KERNEL<16, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;         \
-        default: KERNEL<32, P2, P3><<<grid, block, 0, stream>>>(__VA_ARGS__); break;         \
+#define DISPATCH_LPR3_EX(L, KERNEL, P2, P3, grid, block, stream, a)                              \
+    if ((a).D == (L) * 4) KERNEL<L, P2, P3, true><<<grid, block, 0, stream>>>(a);                \
+    else KERNEL<L, P2, P3, false><<<grid, block, 0, stream>>>(a);
+#define DISPATCH_LPR3(lpr, KERNEL, P2, P3, grid, block, stream, a)                               \
+    switch (lpr) {                                                                               \
+        case 1: KERNEL<1, P2, P3, false><<<grid, block, 0, stream>>>(a); break;                  \
+        case 2: KERNEL<2, P2, P3, false><<<grid, block, 0, stream>>>(a); break;                  \
+        case 4: KERNEL<4, P2, P3, false><<<grid, block, 0, stream>>>(a); break;                  \
+        case 8: DISPATCH_LPR3_EX(8, KERNEL, P2, P3, grid, block, stream, a) break;               \
+        case 16: DISPATCH_LPR3_EX(16, KERNEL, P2, P3, grid, block, stream, a) break;             \
+        default: DISPATCH_LPR3_EX(32, KERNEL, P2, P3, grid, block, stream, a) break;             \
     }
 
 template <int MODE>
