@@ -468,7 +468,7 @@ def main_ours(a):
     step_ms = sum(kb.values())
     traffic = None
     try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01i.json')))
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01j.json')))
         if tr['batch'] == B and tr['dim'] == a.dim:
             traffic = tr['dram_bytes_per_launch'].get(dom)
     except (OSError, ValueError, KeyError):
