@@ -123,6 +123,17 @@ class GpuBackend(object):
         adagrad_dense_(st.bi, st.sbi, db.reshape(-1), st.lr, st.eps)
 
 
+    # ---- adaptive hinge: scores, loss and score gradients as separate calls ----
+    def scores(self, st, cache_rows, cache_bias, u_idx, i_idx):
+        return ops.mf_scores(st.Wu, cache_rows, st.bu.reshape(-1, 1), cache_bias.reshape(-1, 1), u_idx, i_idx)
+
+    def adaptive_loss(self, pos, negmat):
+        """(mean hinge against the column maxima, d/dpos, d/dneg) -- losses.py:127-166."""
+        return ops.pairwise_loss(pos, negmat, None, _lib.LOSS_KIND['adaptive_hinge'])
+
+    def scores_backward(self, st, cache_rows, g, u_idx, i_idx):
+        return ops.mf_scores_backward(g, st.Wu, cache_rows, u_idx, i_idx)
+
     # ---- epoch-level pieces of fit() (all ranks compute the same global stream) ----
     def to_device(self, ids):
         arr = np.ascontiguousarray(ids)
@@ -218,10 +229,8 @@ class ShardedMF(object):
         is owned by this rank).
         """
         if loss == 'adaptive_hinge' or n_neg != 1:
-            # The reference pairs flat negative f = k*B + b with users[f // n] of the
-            # *global* batch (implicit.py:270-275), i.e. with user rows other ranks own;
-            # reproducing that needs a user-row exchange that is not built yet.
-            raise NotImplementedError('sharded adaptive hinge is not supported yet')
+            # the reference's pairing spans the global minibatch: see step_adaptive
+            raise ValueError('adaptive hinge needs the minibatch positions: use step_adaptive')
         if exchange == 'dense' or (exchange == 'auto' and
                                    self._dense_exchange_pays(global_batch // self.plan.world)):
             return self.step_dense(users, items, negs, loss, global_batch, n_neg)
@@ -269,29 +278,22 @@ class ShardedMF(object):
             out.copy_(y[self.rank * chunk:(self.rank + 1) * chunk])
         return out
 
-    def step_a2a(self, users, items, negs, loss, global_batch, n_neg=1):
-        """Per-row routing (the north-star exchange).
-
-        ``users`` must all be owned by this rank (global ids).  Returns the
-        *global* mean loss as a 0-dim tensor (identical on every rank).
-        """
+    def _fetch_rows(self, ids):
+        """Distinct item rows of ``ids`` from their owners (steps 1-3 of the exchange):
+        returns (cache_rows, cache_bias, inverse, n_cache, route) with ``ids[k]`` living
+        in cache row ``inverse[k]``."""
         plan, st, P = self.plan, self.st, self.plan.world
-        B = users.numel()
-        dev = users.device
-        # 1. bucket the distinct item ids by owner
-        ids = torch.cat([items, negs])
-        if B:
+        dev = ids.device
+        if ids.numel():
             uniq, inverse, bounds = self.backend.unique_bucket(ids, plan.num_items, plan.ichunk, P)
-        else:                               # none of this minibatch's users live here: serve peers only
+        else:                               # nothing of this minibatch lives here: serve peers only
             uniq, inverse, bounds = ids, ids, [0] * (P + 1)
         send_counts = [bounds[p + 1] - bounds[p] for p in range(P)]
-        # 2. exchange the request sizes, then the requests
         sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
         rc = torch.empty(P, dtype=torch.int64, device=dev)
         dist.all_to_all_single(rc, sc, group=self.group)
         recv_counts = rc.tolist()
         req = self._a2a(uniq, send_counts, recv_counts)
-        # 3. owners gather rows/biases; rows travel back
         local_req = req - st.ilo
         rows, bias = self.backend.gather(st.Wi, st.bi, local_req)
         n_cache = uniq.numel()
@@ -299,28 +301,114 @@ class ShardedMF(object):
         cap = self.cache_capacity or min(ids.numel(), plan.num_items)
         cache_rows = self._a2a(rows, recv_counts, send_counts)
         cache_bias = self._a2a(bias, recv_counts, send_counts)
-        if cap != n_cache:                 # fixed-capacity cache keeps the kernel workspace layout stable
+        if cap > n_cache:                  # fixed-capacity cache keeps the kernel workspace layout stable
             full = cache_rows.new_zeros((cap, cache_rows.shape[1]))
             full[:n_cache] = cache_rows
             fb = cache_bias.new_zeros(cap)
             fb[:n_cache] = cache_bias
             cache_rows, cache_bias = full, fb
         self.stats['rows_requested'] += n_cache
-        # 4. fused local step (user rows updated in place)
+        return cache_rows, cache_bias, inverse, n_cache, (send_counts, recv_counts, local_req)
+
+    def _return_grads(self, route, g_rows, g_bias):
+        """Item gradients go home; owners reduce in rank order and update their shard."""
+        send_counts, recv_counts, local_req = route
+        g_recv = self._a2a(g_rows.contiguous(), send_counts, recv_counts)
+        gb_recv = self._a2a(g_bias.contiguous(), send_counts, recv_counts)
+        self.backend.owner_update(self.st, local_req, g_recv, gb_recv)
+
+    def _global_loss(self, loss_share):
+        total = loss_share.detach().clone().reshape(1)
+        dist.all_reduce(total, group=self.group)
+        return total.reshape(())
+
+    def step_a2a(self, users, items, negs, loss, global_batch, n_neg=1):
+        """Per-row routing (the north-star exchange).
+
+        ``users`` must all be owned by this rank (global ids).  Returns the
+        *global* mean loss as a 0-dim tensor (identical on every rank).
+        """
+        st = self.st
+        B = users.numel()
+        cache_rows, cache_bias, inverse, n_cache, route = self._fetch_rows(torch.cat([items, negs]))
+        # fused local step (user rows updated in place)
         if B:
             loss_share, g_rows, g_bias = self.backend.local_step(
                 st, cache_rows, cache_bias, n_cache, users - st.ulo, inverse[:B], inverse[B:], loss,
                 global_batch, n_neg)
         else:
             loss_share, g_rows, g_bias = st.bi.new_zeros(()), cache_rows[:0], cache_bias[:0]
-        # 5. item gradients go home; owners reduce in rank order and update their shard
-        g_recv = self._a2a(g_rows, send_counts, recv_counts)
-        gb_recv = self._a2a(g_bias, send_counts, recv_counts)
-        self.backend.owner_update(st, local_req, g_recv, gb_recv)
-        # 6. global loss
-        total = loss_share.detach().clone().reshape(1)
-        dist.all_reduce(total, group=self.group)
-        return total.reshape(())
+        self._return_grads(route, g_rows, g_bias)
+        return self._global_loss(loss_share)
+
+    def step_adaptive(self, users, items, negs_block, bpos, batch_users, n_neg):
+        """Adaptive hinge on a sharded minibatch, with the reference's pairing.
+
+        The reference scores flat negative f of a minibatch with ``users[f // n]`` and
+        reads the result as element ``(k, b) = (f // B, f % B)`` of the ``(n, B)`` matrix
+        whose column maxima enter the hinge (implicit.py:266-275, losses.py:127-166).  So
+        a negative is *scored* where interaction ``f // n`` lives and *consumed* where
+        interaction ``f % B`` lives.  Each rank scores the n-blocks of its own members
+        (``negs_block[j*n:(j+1)*n]`` are flats ``bpos[j]*n ..``), the 4-byte scores travel
+        to the owners of their columns, the loss and the arg-max gradients are formed
+        there, and the gradients travel back the same way.  Rows never move for this:
+        only the usual item-row exchange around it.
+        """
+        plan, st, P = self.plan, self.st, self.plan.world
+        be = self.backend
+        m, Bg, n = users.numel(), batch_users.numel(), int(n_neg)
+        dev = users.device
+        cache_rows, cache_bias, inverse, n_cache, route = self._fetch_rows(torch.cat([items, negs_block]))
+        ul = users - st.ulo
+        ul_rep = ul.repeat_interleave(n)
+        # scores of this rank's members and of their n-blocks
+        if m:
+            pos = be.scores(st, cache_rows, cache_bias, ul, inverse[:m])
+            neg = be.scores(st, cache_rows, cache_bias, ul_rep, inverse[m:])
+        else:
+            pos = st.bi.new_zeros(0)
+            neg = st.bi.new_zeros(0)
+        # flats -> owners of their columns
+        flat = (bpos.repeat_interleave(n) * n + torch.arange(n, device=dev).repeat(m)) if m else bpos
+        dest = torch.div(batch_users[flat % Bg], plan.uchunk, rounding_mode='floor') if m else bpos
+        order = torch.argsort(dest, stable=True)
+        send_counts = torch.bincount(dest, minlength=P)
+        recv_counts_t = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts_t, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts_t.tolist()
+        f_recv = self._a2a(flat[order], sc, rc)
+        s_recv = self._a2a(neg[order], sc, rc)
+        # the (n, m) matrix of this rank's columns, loss, gradients
+        if m:
+            lookup = torch.full((Bg,), -1, dtype=torch.int64, device=dev)
+            lookup[bpos] = torch.arange(m, device=dev)
+            slot = torch.div(f_recv, Bg, rounding_mode='floor') * m + lookup[f_recv % Bg]
+            negmat = s_recv.new_empty(n * m)
+            negmat[slot] = s_recv
+            loss_mean, gp, gn = be.adaptive_loss(pos, negmat.reshape(n, m))
+            # hinge gradients are exactly -/+ 1/B_global wherever they are non-zero: emit that
+            # value itself (not (1/m) * (m/B), which rounds differently per rank), so that
+            # +g and -g meeting on one row cancel exactly as they do in one process
+            inv = float(np.float32(1.0) / np.float32(Bg))
+            loss_share = loss_mean * (m / float(Bg))
+            gp = torch.where(gp != 0, -inv, 0.0).to(torch.float32)
+            g_back = torch.where(gn.reshape(-1)[slot] != 0, inv, 0.0).to(torch.float32)
+        else:
+            loss_share, gp, g_back = st.bi.new_zeros(()), pos, s_recv
+        g_sorted = self._a2a(g_back, rc, sc)
+        # backward of the scores, with the gradient each score earned at its consumer
+        if m:
+            g_neg = torch.empty_like(g_sorted)
+            g_neg[order] = g_sorted
+            dWu, dcache, dbu, dbcache = be.scores_backward(
+                st, cache_rows, torch.cat([gp, g_neg]), torch.cat([ul, ul_rep]), inverse)
+            adagrad_dense_(st.Wu, st.sWu, dWu, st.lr, st.eps)
+            adagrad_dense_(st.bu, st.sbu, dbu.reshape(-1), st.lr, st.eps)
+            g_rows, g_bias = dcache[:n_cache], dbcache.reshape(-1)[:n_cache]
+        else:
+            g_rows, g_bias = cache_rows[:0], cache_bias[:0]
+        self._return_grads(route, g_rows, g_bias)
+        return self._global_loss(loss_share)
 
 
 class SeqShardState(object):
@@ -430,14 +518,15 @@ class ShardedImplicitFactorizationModel(object):
 
     Every rank is handed the same ``Interactions`` (the global shuffle needs all of it);
     parameters and optimizer state are sharded, never replicated.  Optimizer: row-wise
-    Adagrad (``spotlight_b200.optim.fused_adagrad``'s update).  Losses: bpr, hinge,
-    pointwise.
+    Adagrad (``spotlight_b200.optim.fused_adagrad``'s update).  All four losses; adaptive
+    hinge keeps the reference's global negative pairing (:meth:`ShardedMF.step_adaptive`).
     """
 
     def __init__(self, num_users, num_items, rank, world, device, backend=None, loss='bpr',
                  embedding_dim=32, n_iter=10, batch_size=256, learning_rate=0.05, random_state=None,
-                 exchange='auto', init=None, group=None):
-        assert loss in ('pointwise', 'bpr', 'hinge')
+                 exchange='auto', init=None, group=None, num_negative_samples=5):
+        assert loss in ('pointwise', 'bpr', 'hinge', 'adaptive_hinge')
+        self._n_neg = int(num_negative_samples) if loss == 'adaptive_hinge' else 1
         self._loss, self._n_iter, self._batch_size = loss, int(n_iter), int(batch_size)
         self._num_users, self._num_items = int(num_users), int(num_items)
         self._random_state = random_state or np.random.RandomState()
@@ -469,18 +558,28 @@ class ShardedImplicitFactorizationModel(object):
             order = be.shuffled_order(n, self._random_state)
             u, i = be.permute(order, users_dev, items_dev)
             del order
-            negs = be.sample(self._num_items, n, self._random_state)
+            nn = self._n_neg
+            negs = be.sample(self._num_items, n * nn, self._random_state)
             # this rank's members of every minibatch, in minibatch order
             mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
             edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
             bounds = torch.searchsorted(mine, edges).tolist()
-            mu, mi, mn = u[mine], i[mine], negs[mine]
-            del u, i, negs, mine
+            # a minibatch draws len(batch) * n values at once (implicit.py:256-259, 266-275): the
+            # n-block of the member at epoch position p is negs[n*p : n*p + n]
+            mu, mi, mn = u[mine], i[mine], negs.reshape(n, nn)[mine].reshape(-1)
+            bpos = mine % B
+            del i, negs, mine
             losses = []
             for k in range(len(bounds) - 1):
                 sl = slice(bounds[k], bounds[k + 1])
-                losses.append(self.mf.step(mu[sl], mi[sl], mn[sl], self._loss, min(B, n - k * B),
-                                           self._exchange))
+                if self._loss == 'adaptive_hinge':
+                    losses.append(self.mf.step_adaptive(
+                        mu[sl], mi[sl], mn[bounds[k] * nn:bounds[k + 1] * nn], bpos[sl],
+                        u[k * B:(k + 1) * B], nn))
+                else:
+                    losses.append(self.mf.step(mu[sl], mi[sl], mn[sl], self._loss, min(B, n - k * B),
+                                               self._exchange))
+            del u
             epoch_loss = float(torch.stack(losses).mean()) if losses else 0.0
             self.epoch_losses.append(epoch_loss)
             if verbose and self.rank == 0:

@@ -39,6 +39,37 @@ class NumpyBackend(object):
                 torch.from_numpy((r['dWi'] * scale).astype(np.float32))[:n_cache],
                 torch.from_numpy((r['dbi'].reshape(-1) * scale).astype(np.float32))[:n_cache])
 
+    # adaptive hinge pieces
+    def scores(self, st, cache_rows, cache_bias, u_idx, i_idx):
+        Wu, bu = st.Wu.numpy().astype(np.float64), st.bu.numpy().astype(np.float64)
+        Wi, bi = cache_rows.numpy().astype(np.float64), cache_bias.numpy().astype(np.float64)
+        u, i = u_idx.numpy(), i_idx.numpy()
+        return torch.from_numpy(((Wu[u] * Wi[i]).sum(1) + bu[u] + bi[i]).astype(np.float32))
+
+    def adaptive_loss(self, pos, negmat):
+        p, ng = pos.numpy().astype(np.float64), negmat.numpy().astype(np.float64)
+        k = ng.argmax(axis=0)                       # first index on ties, as torch.max
+        hardest = ng[k, np.arange(len(p))]
+        act = ((hardest - p + 1.0) >= 0.0).astype(np.float64)    # sub-gradient 1 at the kink (losses.py:115-124)
+        loss = np.maximum(hardest - p + 1.0, 0.0).mean()
+        gp = -act / float(len(p))
+        gn = np.zeros_like(ng)
+        gn[k, np.arange(len(p))] = act / float(len(p))
+        return (torch.tensor(loss, dtype=torch.float32), torch.from_numpy(gp.astype(np.float32)),
+                torch.from_numpy(gn.astype(np.float32)))
+
+    def scores_backward(self, st, cache_rows, g, u_idx, i_idx):
+        Wu, Wi = st.Wu.numpy().astype(np.float64), cache_rows.numpy().astype(np.float64)
+        u, i, gg = u_idx.numpy(), i_idx.numpy(), g.numpy().astype(np.float64)
+        dWu, dWi = np.zeros_like(Wu), np.zeros_like(Wi)
+        dbu, dbi = np.zeros(len(Wu)), np.zeros(len(Wi))
+        np.add.at(dWu, u, gg[:, None] * Wi[i])
+        np.add.at(dWi, i, gg[:, None] * Wu[u])
+        np.add.at(dbu, u, gg)
+        np.add.at(dbi, i, gg)
+        f = lambda x: torch.from_numpy(x.astype(np.float32))      # noqa: E731
+        return f(dWu), f(dWi), f(dbu), f(dbi)
+
     # epoch-level pieces of the sharded fit(), host NumPy (the reference's own calls)
     def to_device(self, ids):
         return torch.from_numpy(np.ascontiguousarray(ids).astype(np.int64))
@@ -198,7 +229,7 @@ def seq_sharded_run(rank, world, params, batches, loss, lr, device, backend, cnn
     return out, losses, model.stats
 
 
-def reference_epochs(seed, users, items, num_items, B, n_iter):
+def reference_epochs(seed, users, items, num_items, B, n_iter, n_neg=1):
     """The minibatches the reference loop forms (factorization/implicit.py:114,212-259):
     ctor draw, then per epoch shuffle + one randint per minibatch, all from one stream."""
     rs = np.random.RandomState(seed)
@@ -211,7 +242,7 @@ def reference_epochs(seed, users, items, num_items, B, n_iter):
         batches = []
         for lo in range(0, len(u), B):
             bu, bi = u[lo:lo + B].astype(np.int64), i[lo:lo + B].astype(np.int64)
-            batches.append((bu, bi, rs.randint(0, num_items, len(bu), dtype=np.int64)))
+            batches.append((bu, bi, rs.randint(0, num_items, len(bu) * n_neg, dtype=np.int64)))
         epochs.append(batches)
     return epochs, rs
 
@@ -228,7 +259,8 @@ def gather_tables(st, plan, U, I, world):
     return out
 
 
-def sharded_fit_run(rank, world, params, users, items, loss, device, backend, seed, B, n_iter, exchange):
+def sharded_fit_run(rank, world, params, users, items, loss, device, backend, seed, B, n_iter, exchange,
+                    n_neg=5):
     from spotlight_b200.interactions import Interactions
     from spotlight_b200.sharded import ShardedImplicitFactorizationModel
     U, D = params[0].shape
@@ -237,6 +269,7 @@ def sharded_fit_run(rank, world, params, users, items, loss, device, backend, se
     model = ShardedImplicitFactorizationModel(U, I, rank, world, device, backend=backend, loss=loss,
                                               embedding_dim=D, n_iter=n_iter, batch_size=B,
                                               learning_rate=0.05, random_state=rs, exchange=exchange,
-                                              init=[torch.from_numpy(p) for p in params])
+                                              init=[torch.from_numpy(p) for p in params],
+                                              num_negative_samples=n_neg)
     model.fit(Interactions(users, items, num_users=U, num_items=I))
     return gather_tables(model.state, model.plan, U, I, world), model.epoch_losses, rs.get_state()

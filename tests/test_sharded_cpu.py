@@ -129,14 +129,15 @@ def _fit_worker(rank, world, port, loss, exchange, q):
     try:
         params, users, items = _fit_problem()
         out = sc.sharded_fit_run(rank, world, params, users, items, loss, 'cpu', sc.NumpyBackend(),
-                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange)
+                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange, n_neg=3)
         if rank == 0:
             q.put(out)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (3, 'pointwise', 'dense')])
+@pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (3, 'pointwise', 'dense'),
+                                                 (2, 'adaptive_hinge', 'a2a'), (3, 'adaptive_hinge', 'a2a')])
 def test_sharded_fit_is_the_single_process_fit(world, loss, exchange):
     """fit() on N ranks forms the reference's minibatches from the reference's RandomState
     stream (global shuffle, one randint per minibatch), so its trajectory is the
@@ -154,9 +155,10 @@ def test_sharded_fit_is_the_single_process_fit(world, loss, exchange):
         p.join(timeout=60)
         assert p.exitcode == 0
     params, users, items = _fit_problem()
-    epochs, rs = sc.reference_epochs(FIT['seed'], users, items, FIT['I'], FIT['B'], FIT['n_iter'])
+    n_neg = 3 if loss == 'adaptive_hinge' else 1
+    epochs, rs = sc.reference_epochs(FIT['seed'], users, items, FIT['I'], FIT['B'], FIT['n_iter'], n_neg)
     flat = [b for e in epochs for b in e]
-    ref, ref_losses = sc.oracle_run(params, flat, loss, 0.05)
+    ref, ref_losses = sc.oracle_run(params, flat, loss, 0.05, n_neg=n_neg)
     per_epoch = np.array(ref_losses).reshape(FIT['n_iter'], -1).mean(axis=1)
     assert_close(np.array(losses), per_epoch, 1e-5, what='epoch losses')
     for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):

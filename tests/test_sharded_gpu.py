@@ -123,7 +123,7 @@ def _fit_problem():
     return params, rs.randint(0, FIT['U'], FIT['n']).astype(np.int32), rs.randint(0, FIT['I'], FIT['n']).astype(np.int32)
 
 
-def _fit_worker(rank, world, port, exchange, q):
+def _fit_worker(rank, world, port, exchange, q, loss='bpr'):
     import sharded_common as sc
     from spotlight_b200.sharded import GpuBackend
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -133,29 +133,31 @@ def _fit_worker(rank, world, port, exchange, q):
     try:
         params, users, items = _fit_problem()
         dev = torch.device('cuda', rank)
-        out = sc.sharded_fit_run(rank, world, params, users, items, 'bpr', dev, GpuBackend(dev),
-                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange)
+        out = sc.sharded_fit_run(rank, world, params, users, items, loss, dev, GpuBackend(dev),
+                                 FIT['seed'], FIT['B'], FIT['n_iter'], exchange, n_neg=4)
         if rank == 0:
             q.put(out)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('exchange', ['a2a', 'dense'])
-def test_sharded_fit_equals_single_gpu_fit(exchange):
-    """2-GPU fit() vs the single-GPU product fit() from the same RandomState seed and
+@pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (2, 'bpr', 'dense'),
+                                                 (1, 'adaptive_hinge', 'a2a'), (2, 'adaptive_hinge', 'a2a')])
+def test_sharded_fit_equals_single_gpu_fit(world, loss, exchange):
+    """N-GPU fit() vs the single-GPU product fit() from the same RandomState seed and
     weights: same permutation (device shuffle, n >= 2^17), same negatives, same minibatches
-    -> same epoch losses, same final tables, same final generator state."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
+    -> same final tables, same final generator state.  The world-1 case runs the whole
+    sharded code path (bucketing, all-to-alls with itself, score routing of the adaptive
+    hinge) on the product kernels of one GPU."""
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
     from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
     from spotlight_b200.interactions import Interactions
     from spotlight_b200.optim import fused_adagrad
-    world = 2
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 33500 + (os.getpid() * 7) % 2000
-    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, exchange, q)) for r in range(world)]
+    port = 33500 + (os.getpid() * 7 + world) % 2000
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, exchange, q, loss)) for r in range(world)]
     for p in procs:
         p.start()
     got, losses, state = q.get(timeout=300)
@@ -165,8 +167,9 @@ def test_sharded_fit_equals_single_gpu_fit(exchange):
     params, users, items = _fit_problem()
     inter = Interactions(users, items, num_users=FIT['U'], num_items=FIT['I'])
     rs = np.random.RandomState(FIT['seed'])
-    one = ImplicitFactorizationModel(loss='bpr', embedding_dim=FIT['D'], n_iter=FIT['n_iter'],
+    one = ImplicitFactorizationModel(loss=loss, embedding_dim=FIT['D'], n_iter=FIT['n_iter'],
                                      batch_size=FIT['B'], use_cuda=True, random_state=rs,
+                                     num_negative_samples=4,
                                      optimizer_func=fused_adagrad(lr=0.05))
     one._initialize(inter)
     net = one._net
@@ -181,4 +184,4 @@ def test_sharded_fit_equals_single_gpu_fit(exchange):
         assert_close(a, b.reshape(a.shape), 5e-3, what=nm)       # Adagrad trajectory tolerance, as above
     want = rs.get_state()
     assert np.array_equal(state[1], want[1]) and state[2] == want[2]
-    assert len(losses) == FIT['n_iter'] and all(0.0 < v < 1.0 for v in losses)
+    assert len(losses) == FIT['n_iter'] and all(0.0 < v < 1.5 for v in losses)
