@@ -185,14 +185,15 @@ def test_sharded_fit_equals_single_gpu_fit(world, loss, exchange, capsys):
     assert_close(np.array(losses), np.array(single_losses), 2e-5, what='epoch losses')
     for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
         if loss == 'adaptive_hinge':
-            # Measured on the B200 (round 1): the epoch losses of the two paths agree to 2e-5 and
-            # the generator states are identical, but more than 1 % of the rows end further than
-            # 5e-3 apart (max 0.07 on a 0.33 scale).  The two paths score with different kernels
-            # (fused tile forward vs mf_scores + pairwise_loss + mf_scores_backward), and every
-            # arg-max or kink decision that flips moves four rows by a full Adagrad step; whether
-            # that explains all of it is an open item.  Until it is closed the
-            # row-level check is statistical; the exact semantics are pinned on the CPU against
-            # the oracle (tests/test_sharded_cpu.py, worlds 2 and 3).
+            # This trajectory is chaotic at the row level: in the float64 oracle a 1e-7 relative
+            # perturbation of the initial item table moves every user row by more than 1.6e-3
+            # (max 0.05 on a 0.32 scale) within these two epochs, while the epoch losses move by
+            # < 2e-5 (profiles/adaptive_sensitivity.py).  The two GPU paths score with different
+            # kernels (fused tile forward vs mf_scores), i.e. differ by such a perturbation; on
+            # the B200 they agree in the epoch losses (2e-5, asserted above) and the generator
+            # state, with row differences of the same size as the oracle experiment (max 0.07).
+            # The exact semantics are pinned on the CPU against the oracle
+            # (tests/test_sharded_cpu.py, worlds 2 and 3).
             assert np.corrcoef(a.reshape(-1), b.reshape(-1))[0, 1] > 0.9, nm
         else:
             assert_close(a, b.reshape(a.shape), 5e-3, what=nm)   # Adagrad trajectory tolerance, as above
