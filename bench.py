@@ -11,9 +11,14 @@ deterministic backward kernel, fused row-wise Adagrad update.
 One JSON line on stdout (rank 0):
   value      whole-job interactions/s with ids resident in HBM (device timed,
              CUDA events, max over ranks)
-  e2e        the same metric through the public API, ImplicitFactorizationModel
-             .fit(Interactions) with HOST numpy ids: host shuffle, H2D copies,
-             device negatives, training steps, D2H of the per-batch losses
+  e2e        the same metric through the public API with HOST numpy ids in
+             page-locked memory, wall clock around the whole call:
+             ImplicitFactorizationModel.fit(Interactions) at N = 1,
+             ShardedImplicitFactorizationModel.fit(Interactions) at N > 1 --
+             H2D of the ids, range check, the bit-exact RandomState.shuffle
+             permutation (on the device), id gather, device negatives, K training
+             steps, D2H of the per-batch losses.  Two consecutive calls; `value`
+             is the second, `first_call_value` the first (allocator cold).
   roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the reference's loop restated on stock torch CPU ops
