@@ -144,3 +144,28 @@ def test_cnn_step_golden(name):
     for i in range(L):
         assert_close(r['dconvs'][i][0], g['grad.cnn_%d.weight' % i], 1e-5, what='dW%d' % i)
         assert_close(r['dconvs'][i][1], g['grad.cnn_%d.bias' % i], 1e-5, what='db%d' % i)
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 17, 100, 1000, 4097, 100000])
+def test_parallel_shuffle_formulation_matches_numpy(n):
+    """The fixed-point / link-and-chase formulation csrc/shuffle.cu implements, restated in
+    oracle/shuffle.py, is RandomState.shuffle (torch_utils.py:46-47): same permutation, same
+    number of stream words consumed."""
+    from oracle import shuffle as osh
+    for seed in (0, 7):
+        rs = np.random.RandomState(seed)
+        rs.randint(0, 100, 33)                                   # mid-block start
+        probe = np.random.RandomState()
+        probe.set_state(rs.get_state())
+        words = probe.randint(0, 2 ** 32, 2 * n + 64, dtype=np.uint64).astype(np.uint32)
+        j, used = osh.resolve_draws(words, n)
+        got = osh.apply_swaps(j)
+        want = np.arange(n)
+        rs.shuffle(want)
+        assert np.array_equal(got, want)
+        probe2 = np.random.RandomState(seed)                     # consume exactly `used` words
+        probe2.randint(0, 100, 33)
+        if used:
+            probe2.randint(0, 2 ** 32, used, dtype=np.uint64)
+        assert np.array_equal(probe2.get_state()[1], rs.get_state()[1])
+        assert probe2.get_state()[2] == rs.get_state()[2]
