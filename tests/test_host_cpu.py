@@ -146,3 +146,37 @@ def test_sample_items_host_path_is_numpy():
     from spotlight_b200.sampling import sample_items
     r1, r2 = np.random.RandomState(9), np.random.RandomState(9)
     assert (sample_items(1683, (4, 5), r1) == r2.randint(0, 1683, (4, 5), dtype=np.int64)).all()
+
+
+def test_shuffle_stream_budget_covers_consumption():
+    """rng.shuffle_begin sizes the stream as E[words] + 8 sigma: check the expectation and
+    the margin against the words RandomState.shuffle really consumes (oracle/shuffle.py)."""
+    import math
+    from oracle import shuffle as osh
+    from spotlight_b200.rng import _shuffle_expected_words
+    for n in (2, 3, 10, 1000, 4097, 65537, 300000):
+        used = []
+        for seed in range(6):
+            rs = np.random.RandomState(seed)
+            words = rs.randint(0, 2 ** 32, 2 * n + 64, dtype=np.uint64).astype(np.uint32)
+            used.append(osh.resolve_draws(words, n)[1])
+        budget = _shuffle_expected_words(n) + 8.0 * math.sqrt(2.0 * n) + 64
+        assert max(used) <= budget
+        assert abs(np.mean(used) - _shuffle_expected_words(n)) <= 4.0 * math.sqrt(2.0 * n / 6) + 2
+
+
+def test_every_entry_point_is_documented():
+    """Each exported slb_* symbol is declared in include/spotlight_b200.h and has a row in
+    INTEGRATION.md's entry-point table (what it replaces in the reference)."""
+    import re
+    from conftest import ROOT
+    from spotlight_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'spotlight_b200.h')).read()
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    declared = set(re.findall(r'\b(slb_[a-z0-9_]+)\s*\(', header))
+    assert set(_lib.EXPORTS) <= declared
+    prefixes = re.findall(r'`(slb_[a-z_]+_)`', doc)          # the workspace_bytes family row
+    undocumented = [name for name in _lib.EXPORTS if name not in doc and
+                    not (name.endswith('_workspace_bytes') and
+                         any(name == p + 'workspace_bytes' for p in prefixes))]
+    assert not undocumented, undocumented
