@@ -321,6 +321,43 @@ __device__ __forceinline__ void pf_row_l2(const float* row, int D) {
     for (int o = 0; o < D * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
 }
 
+// BWD_BULK (default 0; round-2 experiment, built only through profiles/run_variants.sh):
+// the user-side kernel (MODE 2, exact row width) stages the weight / optimizer-state rows of a
+// whole 32-segment tile in shared memory with one cp.async.bulk per row, completion on one
+// mbarrier per warp -- 16 KB in flight per warp without holding a register.  NOT yet run on
+// hardware: it compiles for sm_100a (SASS: UBLKCP) and is off in the shipped library.
+#ifndef BWD_BULK
+#define BWD_BULK 0
+#endif
+#if BWD_BULK
+__device__ __forceinline__ uint32_t bulk_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void bulk_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bulk_smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_bar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bulk_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bulk_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bulk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_bar_wait(uint64_t* bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bulk_smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();                               // a lost copy must not hang the GPU box
+}
+#endif
+
 #ifndef BWD_MINB
 #define BWD_MINB 6
 #endif
@@ -345,6 +382,19 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
     // EX: the row is exactly one 128-bit load per lane (D == 4 * LPR), so D is a compile-time
     // constant: no column loop, shifts for the row offsets (B200, D = 64: step 476 -> 431 us)
     const int D = EX ? LPR * 4 : a.D;
+#if BWD_BULK
+    constexpr bool BULK = MODE == 2 && EX && TI == 32;
+    constexpr int RB = LPR * 16;                                  // bytes per row
+    extern __shared__ __align__(128) unsigned char bulk_rows[];   // WARPS x TI x 2 x RB
+    __shared__ uint64_t bulk_bar[WARPS];
+    unsigned char* my_rows = bulk_rows + (threadIdx.x >> 5) * (TI * 2 * RB);
+    uint64_t* my_bar = &bulk_bar[threadIdx.x >> 5];
+    uint32_t bulk_phase = 0;
+    if (BULK) {
+        if (lane == 0) bulk_bar_init(my_bar);
+        __syncwarp();
+    }
+#endif
     const int nseg = a.seg.totals[0];
     const int nsegA = a.seg.totals[2];
     if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0 && a.compact_counts) {
@@ -366,11 +416,32 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
         int start = 0, len = 0, row = 0;
         int p[BWD_FAST] = {};
         float g[BWD_FAST] = {};
+#if BWD_BULK
         if (valid) {
-            const bool isA = sidx < nsegA;
             start = a.seg.seg_start[sidx];
             len = a.seg.seg_start[sidx + 1] - start;
             row = a.seg.seg_row[sidx];
+        }
+        if (BULK) {
+            const bool stage = valid && len <= CAP && row != a.frozen_a;
+            const unsigned who = __ballot_sync(0xffffffffu, stage);
+            const uint32_t per = a.opt == SLB_OPT_ADAGRAD ? 2u * RB : 1u * RB;
+            if (lane == 0) bulk_bar_expect(my_bar, __popc(who) * per);
+            __syncwarp();
+            if (stage) {
+                bulk_g2s(my_rows + lane * 2 * RB, a.Wu + static_cast<int64_t>(row) * D, RB, my_bar);
+                if (a.opt == SLB_OPT_ADAGRAD)
+                    bulk_g2s(my_rows + lane * 2 * RB + RB, a.sWu + static_cast<int64_t>(row) * D, RB, my_bar);
+            }
+        }
+#endif
+        if (valid) {
+            const bool isA = sidx < nsegA;
+#if !BWD_BULK
+            start = a.seg.seg_start[sidx];
+            len = a.seg.seg_start[sidx + 1] - start;
+            row = a.seg.seg_row[sidx];
+#endif
             if (len <= BWD_FAST) {
                 int m[BWD_FAST];
 #pragma unroll
@@ -383,6 +454,9 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
                     if (k < len) { g[k] = t_g[m[k]]; p[k] = pidx[m[k]]; }
             }
         }
+#if BWD_BULK
+        if (BULK) { bulk_bar_wait(my_bar, bulk_phase); bulk_phase ^= 1u; }
+#endif
         for (int it = 0; it < ITERS; ++it) {
             const int src = it * GPW + grp;               // >= TI only when TI < GPW: idle group
             const int s_len = __shfl_sync(0xffffffffu, len, src & 31);
@@ -442,6 +516,13 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 float b2 = 0.f;
                 float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = w4;
+#if BWD_BULK
+                if (BULK) {
+                    const unsigned char* staged = my_rows + src * 2 * RB + c * 4;
+                    w4 = *reinterpret_cast<const float4*>(staged);
+                    if (srow) s4 = *reinterpret_cast<const float4*>(staged + RB);
+                } else
+#endif
                 if (MODE == 2) { w4 = ld4(wrow + c); if (srow) s4 = ld4(srow + c); }
                 if (s_len <= BWD_FAST) {
                     float4 v[BWD_FAST];
@@ -509,6 +590,9 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
                 }
             }
         }
+#if BWD_BULK
+        if (BULK) __syncwarp();             // the next tile's copies overwrite the staged rows
+#endif
     }
 }
 
@@ -1055,7 +1139,19 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<items>");
             launch_long<1>(lpr, st, a);
             SLB_LAUNCH_CHECK("mf_bwd_long_kernel<items>");
-            BWD_TILE(2);
+#if BWD_BULK
+            if (lpr == 16 && a.D == 64 && !bsmall) {
+                auto kern = mf_bwd_tile_kernel<16, 2, 32, true>;
+                constexpr int BULK_SMEM = (MF_TILE_THREADS / 32) * 32 * 2 * 256;
+                static bool configured = false;
+                if (!configured) {
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM);
+                    configured = true;
+                }
+                kern<<<tgrid, MF_TILE_THREADS, BULK_SMEM, st>>>(a);
+            } else
+#endif
+            { BWD_TILE(2); }
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
             launch_long<2>(lpr, st, a);
             SLB_LAUNCH_CHECK("mf_bwd_long_kernel<users+opt>");
