@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds variants/lib_<name>.so: the shipped library with mf.cu recompiled under extra -D switches
-# (experiment knobs in csrc/mf.cu: GEN_CHUNK, BWD_MINB, BWD_MINB1, BWD_FAST, BWD_BULK).
+# (experiment knobs in csrc/mf.cu: GEN_CHUNK, BWD_MINB, BWD_MINB1, BWD_FAST, BWD_BULK, BWD_OPT_CT=2 for Adagrad).
 # Usage: bash profiles/build_variant.sh bulk "-DBWD_BULK=1"   then   gpurun -- 'bash profiles/run_variants.sh base bulk'
 set -e
 name=$1; flags=$2

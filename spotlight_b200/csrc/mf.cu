@@ -382,6 +382,12 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
     // EX: the row is exactly one 128-bit load per lane (D == 4 * LPR), so D is a compile-time
     // constant: no column loop, shifts for the row offsets (B200, D = 64: step 476 -> 431 us)
     const int D = EX ? LPR * 4 : a.D;
+#if defined(BWD_OPT_CT)
+    // round-2 experiment (off unless -DBWD_OPT_CT=<SLB_OPT_* value>): the optimizer kind is a
+    // compile-time constant and weight decay is assumed zero, so the update's branches fold
+    a.opt = BWD_OPT_CT;
+    a.wd = 0.f;
+#endif
 #if BWD_BULK
     constexpr bool BULK = MODE == 2 && EX && TI == 32;
     constexpr int RB = LPR * 16;                                  // bytes per row
