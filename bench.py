@@ -21,18 +21,18 @@ One JSON line on stdout (rank 0):
              is the second, `first_call_value` the first (allocator cold).
   roofline   dominant kernel: algorithmic bytes / CUDA-event duration vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's loop restated on stock torch CPU ops
-             (oracle/torch_port.py, kind "port") timed on this box's host cores
-             on a bounded sample of the same workload
+  cpu_baseline  the unmodified reference (baseline/_ref, kind "reference"; the
+             torch-CPU restatement oracle/torch_port.py, kind "port", only if the
+             install is absent) timed on this box's host cores on a bounded sample
+             of the same workload
 
-``--impl reference`` times only that CPU port (all host threads) on the same
+``--impl reference`` times only that CPU arm (all host threads) on the same
 config and prints the same line shape with "impl": "reference".
 """
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -81,58 +81,154 @@ def workload_config(a, n_gpus):
 # --------------------------------------------------------------------------
 
 class ClockSampler(object):
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled in-process through NVML (nvidia_ml_py).
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    NVML is initialised and the sampling thread started well BEFORE the warm-up; only
+    samples whose timestamp falls inside [mark_begin, mark_end] are reported.  (Round 1
+    spawned `nvidia-smi -lms` right before the timed region, so its start-up -- NVML
+    attaching to every GPU of the node -- ran inside a 12 ms timed region; that is the
+    prime suspect for the one-off ~65 ms stall the 8-GPU node showed.  Nothing is spawned
+    or initialised near the timed region any more.)
+    """
+    NAMES = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+             ('sw_power_cap', 0x4))
+
+    def __init__(self, index=0, period_s=0.001):
+        self.index, self.period = index, period_s
+        self.samples, self.t0, self.t1 = [], None, None
+        self._stop = threading.Event()
+        self._thread, self._h, self._nv = None, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '20'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() \
+                    else self.index
+                h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._nv, self._h = nv, h
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as exc:            # no NVML: the line says so instead of inventing clocks
+            self._err = repr(exc)[:200]
+        return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+    def _run(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
-                          for i in range(4) if r[2 + i].lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self._thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0,
+                    'error': getattr(self, '_err', 'NVML unavailable')}
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= self.t1]
+        note = None
+        if not inside and self.samples and self.t0 is not None:
+            # region shorter than the sampling period: the two samples that bracket it
+            before = [x for x in self.samples if x[0] < self.t0][-1:]
+            after = [x for x in self.samples if x[0] > self.t1][:1]
+            inside, note = before + after, 'region shorter than the sampling period: bracketing samples'
+        sm = [x[1] for x in inside]
+        bits = 0
+        for x in inside:
+            bits |= x[2]
+        out = {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+               'reasons': sorted(n for n, b in self.NAMES if bits & b), 'samples': len(sm),
+               'source': 'NVML in-process, %.0f ms period, started before warm-up' % (self.period * 1e3)}
+        if note:
+            out['note'] = note
+        return out
 
 
 # --------------------------------------------------------------------------
 # CPU port (cpu_baseline and the reference arm)
 # --------------------------------------------------------------------------
 
-def run_cpu_port(a, steps, warmup):
-    """interactions/s of the reference loop restated on torch CPU ops.
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
 
-    "All the host threads it can use": ATen's embedding backward / optimizer
-    kernels stop scaling (and regress) well before 100+ threads, so one step is
-    timed at a few thread counts and the fastest setting is used for the run.
-    """
+
+def _reference_runner(a):
+    """fit_steps(lo, nsteps) on the UNMODIFIED reference (baseline/_ref, pip-installed from
+    /root/reference: `spotlight.factorization.implicit.ImplicitFactorizationModel.fit` on CPU
+    through its own public API), or None when the install is not on this box."""
+    if not os.path.isdir(os.path.join(REF_DIR, 'spotlight')):
+        return None
+    import torch
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from spotlight.factorization.implicit import ImplicitFactorizationModel as RefModel
+        from spotlight.interactions import Interactions as RefInteractions
+    except Exception:
+        return None
+    model = RefModel(loss=a.loss, embedding_dim=a.dim, n_iter=1, batch_size=a.batch, learning_rate=a.lr,
+                     optimizer_func=lambda p: torch.optim.Adagrad(p, lr=a.lr), use_cuda=False,
+                     random_state=np.random.RandomState(42))
+
+    def fit_steps(users, items, nsteps):
+        n = nsteps * a.batch
+        model.fit(RefInteractions(users[:n].astype(np.int32), items[:n].astype(np.int32),
+                                  num_users=a.users, num_items=a.items))
+    return fit_steps
+
+
+def _port_runner(a):
     import torch
     from oracle import torch_port
-    ncpu = os.cpu_count() or 1
     torch.manual_seed(0)
     net = torch_port.PortBilinearNet(a.users, a.items, a.dim)
     opt = torch.optim.Adagrad(net.parameters(), lr=a.lr)
+    rs = np.random.RandomState(0)
+
+    def fit_steps(users, items, nsteps):
+        torch_port.fit_steps(net, opt, users, items, a.items, a.batch, a.loss, rs, max_steps=nsteps)
+    return fit_steps
+
+
+def run_cpu_port(a, steps, warmup):
+    """interactions/s of the reference's CPU fit() loop on this box's host cores.
+
+    kind "reference": the unmodified reference from baseline/_ref (stock code path, its own
+    shuffle, sampler, autograd and the same Adagrad optimizer handed in through its
+    `optimizer_func`); kind "port": oracle/torch_port.py, the same loop restated on stock
+    torch CPU ops, when the install is absent.
+    "All the host threads it can use": ATen's embedding backward / optimizer kernels stop
+    scaling (and regress) well before 100+ threads, so one step is timed at a few thread
+    counts and the fastest setting is used for the run.
+    """
+    import torch
+    ncpu = os.cpu_count() or 1
+    fit_steps, kind = _reference_runner(a), 'reference'
+    if fit_steps is None:
+        fit_steps, kind = _port_runner(a), 'port'
     rs = np.random.RandomState(0)
     B = a.batch
     cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
@@ -141,25 +237,27 @@ def run_cpu_port(a, steps, warmup):
     items = rs.randint(0, a.items, n).astype(np.int64)
     torch.set_num_threads(cands[-1])
     lo = warmup * B
-    torch_port.fit_steps(net, opt, users[:lo], items[:lo], a.items, B, a.loss, rs, max_steps=warmup)
+    fit_steps(users[:lo], items[:lo], warmup)
     best, best_t = cands[-1], None
     for c in cands:
         torch.set_num_threads(c)
         t0 = time.perf_counter()
-        torch_port.fit_steps(net, opt, users[lo:lo + B], items[lo:lo + B], a.items, B, a.loss, rs,
-                             max_steps=1)
+        fit_steps(users[lo:lo + B], items[lo:lo + B], 1)
         dt = time.perf_counter() - t0
         lo += B
         if best_t is None or dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
     t0 = time.perf_counter()
-    torch_port.fit_steps(net, opt, users[lo:], items[lo:], a.items, B, a.loss, rs, max_steps=steps)
+    fit_steps(users[lo:], items[lo:], steps)
     dt = time.perf_counter() - t0
-    return {'value': steps * B / dt, 'unit': UNIT, 'cores': best, 'kind': 'port',
+    what = ('unmodified reference (baseline/_ref: spotlight.factorization.implicit.'
+            'ImplicitFactorizationModel.fit, use_cuda=False)' if kind == 'reference'
+            else 'reference loop restated on torch CPU ops (oracle/torch_port.py)')
+    return {'value': steps * B / dt, 'unit': UNIT, 'cores': best, 'kind': kind,
             'sample': '%d steps of batch %d after %d warm-up, torch %s CPU with %d of %d host '
-                      'threads (fastest of %s), Adagrad dense (reference loop, '
-                      'oracle/torch_port.py)' % (steps, B, warmup, torch.__version__, best, ncpu, cands),
+                      'threads (fastest of %s), Adagrad dense, %s'
+                      % (steps, B, warmup, torch.__version__, best, ncpu, cands, what),
             'ms_per_step': dt / steps * 1e3}
 
 
@@ -323,12 +421,12 @@ def main_sharded(a, rank, world, local):
             last = model.step(users[s], items[s], negs[s], a.loss, world * B, a.exchange)
         return last
 
+    sampler = ClockSampler(local).start() if rank == 0 else None
     run(0, W)
     dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     model.stats = {'rows_requested': 0, 'bytes_a2a': 0}
     e0.record()
@@ -336,6 +434,8 @@ def main_sharded(a, rank, world, local):
     e1.record()
     dist.barrier()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.mark_end()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -382,6 +482,7 @@ def main_ours(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         return main_sharded(a, rank, world, local)
+    sampler = ClockSampler(local).start() if rank == 0 else None      # long before the timed region
     model = build_model(a, local)
     dev = torch.device('cuda', local)
     B, K, W = a.batch, a.steps, a.warmup
@@ -404,15 +505,16 @@ def main_ours(a):
     with torch.cuda.stream(_side_stream(dev)):
         _rng.reserve(a.items, min(64, K) * B, dev)
     del _prime
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     epoch_loss = model._run_epoch_device(users[W * B:], items[W * B:])  # exactly K steps
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)

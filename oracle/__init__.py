@@ -12,10 +12,14 @@ Contents (every function cites the reference file:line it restates):
 * ``murmur``    -- MurmurHash3_x86_32 as used by ``BloomEmbedding``.
 * ``mf``        -- BilinearNet forward / the four losses / closed-form backward.
 * ``seq``       -- PoolNet and CNNNet forward / backward closed forms.
+* ``shuffle``   -- ``RandomState.shuffle`` (Fisher-Yates on the same stream).
 * ``torch_port``-- the reference's fit() loop restated on stock torch CPU ops
-                   (the timed ``cpu_baseline`` "port").
-* ``c/``        -- plain-C restatement of the integer parts and the MF step,
-                   compiled by ``__graft_entry__.build()`` into ``oracle/_c``.
+                   (the timed ``cpu_baseline`` "port", used by bench.py only when
+                   the unmodified reference is not installed under
+                   ``baseline/_ref``).
+
+The reference is pure Python (no C sources to compile into ``oracle/_ref``); the
+restatements are NumPy, so there is no C build step for the oracle.
 
 Parity pinning: the restatements are checked (tests/test_oracle_*.py) against
 golden vectors produced by the *live* reference in the build container

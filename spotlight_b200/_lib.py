@@ -24,8 +24,9 @@ OPT_NONE, OPT_SGD, OPT_ADAGRAD = 0, 1, 2
 # every symbol include/spotlight_b200.h declares
 EXPORTS = (
     'slb_version', 'slb_last_error', 'slb_sm_count', 'slb_workspace_init',
-    'slb_mt19937_fill', 'slb_mt19937_fill_parallel', 'slb_host_shuffle_order',
-    'slb_sample_workspace_bytes', 'slb_sample_bounded',
+    'slb_mt19937_fill', 'slb_mt19937_fill_parallel', 'slb_mt19937_direct_slots',
+    'slb_mt19937_fill_direct', 'slb_host_shuffle_order',
+    'slb_sample_workspace_bytes', 'slb_sample_bounded', 'slb_sample_bounded_chain',
     'slb_shuffle_workspace_bytes', 'slb_shuffle_order', 'slb_permute_ids',
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
@@ -101,6 +102,10 @@ def _declare(lib):
     lib.slb_workspace_init.argtypes = [c_vp, c_sz, c_vp]
     lib.slb_mt19937_fill.argtypes = [c_vp, c_i64, c_vp]
     lib.slb_mt19937_fill_parallel.argtypes = [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]
+    lib.slb_mt19937_direct_slots.argtypes = [c_i64, c_i32]
+    lib.slb_mt19937_direct_slots.restype = c_i64
+    lib.slb_mt19937_fill_direct.argtypes = [c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]
+    lib.slb_sample_bounded_chain.argtypes = [c_vp, c_i64, c_vp, ctypes.c_uint32, c_i64, c_vp, c_vp, c_sz, c_vp]
     lib.slb_host_shuffle_order.argtypes = [c_vp, c_vp, c_i64, c_i32, c_vp]
     lib.slb_shuffle_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_shuffle_workspace_bytes.restype = c_sz

@@ -105,16 +105,10 @@ mt19937_fill_par_kernel(uint32_t* blocks, const uint32_t* __restrict__ states, i
 // blocks into states[(c << (m+1)) + (1 << m)].
 constexpr int JUMP_THREADS = 640;
 
-__global__ void __launch_bounds__(JUMP_THREADS)
-mt19937_jump_kernel(uint32_t* states, const uint32_t* __restrict__ blocks0,
-                    const uint32_t* __restrict__ poly, int m, int P) {
-    __shared__ uint32_t E[MT_N + 32];
-    __shared__ uint32_t acc[MT_N];
+// acc <- g(T) in, g given as 624 coefficient words; result written to out[0..624).
+__device__ __forceinline__ void mt_jump_apply(const uint32_t* __restrict__ in, const uint32_t* __restrict__ poly,
+                                              uint32_t* __restrict__ out, uint32_t* E, uint32_t* acc) {
     const int t = threadIdx.x;
-    const int src_r = blockIdx.x << (m + 1);
-    const int dst_r = src_r + (1 << m);
-    if (dst_r >= P) return;
-    const uint32_t* in = src_r == 0 ? blocks0 : states + static_cast<int64_t>(src_r) * MT_N;
     if (t < MT_N) { E[t] = in[t]; acc[t] = 0u; }
     __syncthreads();
     if (t < 32) E[MT_N + t] = mt_mix(E[t], E[t + 1], E[t + MT_M]);
@@ -143,8 +137,37 @@ mt19937_jump_kernel(uint32_t* states, const uint32_t* __restrict__ blocks0,
         }
         __syncthreads();
     }
-    uint32_t* out = states + static_cast<int64_t>(dst_r) * MT_N;
     if (t < MT_N) { int i = o + t; if (i >= MT_N) i -= MT_N; out[t] = acc[i]; }
+}
+
+// Doubling round m over state slots that are `scale` apart: CTA c jumps slot
+// (c << (m+1)) * scale by the polynomial handed in into slot that + (1 << m) * scale.
+__global__ void __launch_bounds__(JUMP_THREADS)
+mt19937_jump_kernel(uint32_t* states, const uint32_t* __restrict__ blocks0,
+                    const uint32_t* __restrict__ poly, int m, int P, int scale) {
+    __shared__ uint32_t E[MT_N + 32];
+    __shared__ uint32_t acc[MT_N];
+    const int64_t src_r = static_cast<int64_t>(blockIdx.x << (m + 1)) * scale;
+    const int64_t dst_r = src_r + static_cast<int64_t>(1 << m) * scale;
+    if (dst_r >= P) return;
+    const uint32_t* in = src_r == 0 ? blocks0 : states + src_r * MT_N;
+    mt_jump_apply(in, poly, states + dst_r * MT_N, E, acc);
+}
+
+// Direct round: slot c * R + r (r = 1..R-1) = slot c * R jumped by r * J0 blocks, with the
+// precomputed polynomial x^(624 * J0 * r) (row r - 1 of the direct table).  One launch,
+// every CTA independent.
+__global__ void __launch_bounds__(JUMP_THREADS)
+mt19937_jump_direct_kernel(uint32_t* states, const uint32_t* __restrict__ blocks0,
+                           const uint32_t* __restrict__ direct, int R, int P) {
+    __shared__ uint32_t E[MT_N + 32];
+    __shared__ uint32_t acc[MT_N];
+    const int c = blockIdx.x / (R - 1), r = blockIdx.x % (R - 1) + 1;
+    const int64_t src_r = static_cast<int64_t>(c) * R;
+    const int64_t dst_r = src_r + r;
+    if (dst_r >= P) return;
+    const uint32_t* in = src_r == 0 ? blocks0 : states + src_r * MT_N;
+    mt_jump_apply(in, direct + static_cast<int64_t>(r - 1) * MT_N, states + dst_r * MT_N, E, acc);
 }
 
 constexpr int SMP_THREADS = 256;
@@ -246,6 +269,30 @@ __global__ void sample_commit_kernel(int64_t* cursor, const int64_t* result) {
     cursor[1] = result[1];
 }
 
+// Commit + hand-over on the device: the block holding the next unread word becomes block 0
+// and the cursor its position in it, exactly what RandomState.set_state would be given
+// (numpy leaves pos = 624 on a block boundary).  cursor[2] counts draws that ran out of
+// stream words, cursor[3] the values produced since the stream was opened.
+__global__ void __launch_bounds__(640)
+sample_rebase_kernel(uint32_t* blocks, int64_t nwords, int64_t* cursor, const int64_t* result, int64_t count) {
+    __shared__ uint32_t tmp[MT_N];
+    const int64_t end = result[0], produced = result[1];
+    int64_t blk, pos;
+    if (end >= nwords) { blk = nwords / MT_N - 1; pos = MT_N; }
+    else if (end % MT_N == 0 && end > 0) { blk = end / MT_N - 1; pos = MT_N; }
+    else { blk = end / MT_N; pos = end % MT_N; }
+    const int t = threadIdx.x;
+    if (t < MT_N) tmp[t] = blocks[blk * MT_N + t];
+    __syncthreads();
+    if (t < MT_N) blocks[t] = tmp[t];
+    if (t == 0) {
+        cursor[0] = pos;
+        cursor[1] = produced;
+        if (produced < count) cursor[2] += 1;
+        cursor[3] += produced;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -289,11 +336,56 @@ int slb_mt19937_fill_parallel(uint32_t* blocks, int64_t nblocks, const uint32_t*
             const int grid = (P - (1 << m) + (1 << (m + 1)) - 1) >> (m + 1);
             if (grid <= 0) continue;
             mt19937_jump_kernel<<<grid, JUMP_THREADS, 0, st>>>(states, blocks,
-                                                               jump_table + static_cast<int64_t>(k + m) * MT_N, m, P);
+                                                               jump_table + static_cast<int64_t>(k + m) * MT_N, m, P, 1);
             SLB_LAUNCH_CHECK("mt19937_jump_kernel");
         }
     }
     mt19937_fill_par_kernel<<<P, 256, 0, st>>>(blocks, states, J, nblocks);
+    SLB_LAUNCH_CHECK("mt19937_fill_par_kernel");
+    return SLB_OK;
+}
+
+int64_t slb_mt19937_direct_slots(int64_t nblocks, int32_t j0_log2) {
+    const int64_t J0 = 1ll << j0_log2;
+    return nblocks <= 1 ? 1 : (nblocks - 1 + J0 - 1) / J0;
+}
+
+int slb_mt19937_fill_direct(uint32_t* blocks, int64_t nblocks, const uint32_t* jump_table,
+                            int32_t table_rows, const uint32_t* direct_table, int32_t direct_rows,
+                            int32_t j0_log2, uint32_t* states, int64_t state_slots, slb_stream_t stream) {
+    SLB_REQUIRE(blocks && jump_table && direct_table && states && nblocks >= 1, "mt19937_fill_direct: bad arguments");
+    SLB_REQUIRE(direct_rows >= 1 && j0_log2 >= 0 && j0_log2 < 20, "mt19937_fill_direct: bad table shape");
+    if (nblocks == 1) return SLB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t J0 = 1ll << j0_log2;
+    const int R = direct_rows + 1;                                   // fine slots per coarse slot
+    const int64_t P64 = (nblocks - 1 + J0 - 1) / J0;                 // fine slots (CTAs of the fill)
+    SLB_REQUIRE(P64 <= state_slots && P64 < (1ll << 30), "mt19937_fill_direct: %lld state slots needed, %lld given",
+                static_cast<long long>(P64), static_cast<long long>(state_slots));
+    const int P = static_cast<int>(P64);
+    const int C = (P + R - 1) / R;                                   // coarse slots
+    if (C > 1) {
+        // coarse slots are R * J0 blocks apart: doubling rounds with the power-of-two table
+        int kc = j0_log2;
+        while ((1 << (kc - j0_log2)) < R) ++kc;
+        SLB_REQUIRE((1 << (kc - j0_log2)) == R, "mt19937_fill_direct: direct_rows + 1 must be a power of two");
+        int top = 0;
+        while ((1 << (top + 1)) < C) ++top;
+        SLB_REQUIRE(kc + top < table_rows, "mt19937_fill_direct: jump table too small for %lld blocks",
+                    static_cast<long long>(nblocks));
+        for (int m = top; m >= 0; --m) {
+            const int grid = (C - (1 << m) + (1 << (m + 1)) - 1) >> (m + 1);
+            if (grid <= 0) continue;
+            mt19937_jump_kernel<<<grid, JUMP_THREADS, 0, st>>>(states, blocks,
+                                                               jump_table + static_cast<int64_t>(kc + m) * MT_N, m, P, R);
+            SLB_LAUNCH_CHECK("mt19937_jump_kernel");
+        }
+    }
+    if (P > 1) {
+        mt19937_jump_direct_kernel<<<C * (R - 1), JUMP_THREADS, 0, st>>>(states, blocks, direct_table, R, P);
+        SLB_LAUNCH_CHECK("mt19937_jump_direct_kernel");
+    }
+    mt19937_fill_par_kernel<<<P, 256, 0, st>>>(blocks, states, J0, nblocks);
     SLB_LAUNCH_CHECK("mt19937_fill_par_kernel");
     return SLB_OK;
 }
@@ -307,12 +399,13 @@ size_t slb_sample_workspace_bytes(int64_t nwords) {
     return ws.bytes();
 }
 
-int slb_sample_bounded(const uint32_t* blocks, int64_t nwords, int64_t* cursor, uint32_t rng,
-                       int64_t count, int64_t* out, void* workspace, size_t workspace_bytes,
-                       slb_stream_t stream) {
+static int sample_bounded_impl(uint32_t* blocks, int64_t nwords, int64_t* cursor, uint32_t rng,
+                               int64_t count, int64_t* out, void* workspace, size_t workspace_bytes,
+                               bool chain, slb_stream_t stream) {
     SLB_REQUIRE(blocks && cursor && out && workspace, "sample_bounded: null pointer");
     SLB_REQUIRE(count > 0 && nwords > 0, "sample_bounded: count and nwords must be > 0");
     SLB_REQUIRE(rng != 0 && rng != 0xffffffffu, "sample_bounded: rng must be in [1, 2^32 - 2]");
+    SLB_REQUIRE(!chain || nwords % MT_N == 0, "sample_bounded_chain: nwords must be whole blocks");
     if (workspace_bytes < slb_sample_workspace_bytes(nwords)) {
         slb_set_error("sample_bounded: workspace too small");
         return SLB_ENOSPC;
@@ -333,9 +426,27 @@ int slb_sample_bounded(const uint32_t* blocks, int64_t nwords, int64_t* cursor, 
     sample_scatter_kernel<<<static_cast<unsigned>(ntiles), SMP_THREADS, 0, st>>>(blocks, nwords, cursor, rng, mask, count,
                                                                  tile_off, ntiles, out, result);
     SLB_LAUNCH_CHECK("sample_scatter_kernel");
-    sample_commit_kernel<<<1, 1, 0, st>>>(cursor, result);
-    SLB_LAUNCH_CHECK("sample_commit_kernel");
+    if (chain) {
+        sample_rebase_kernel<<<1, 640, 0, st>>>(blocks, nwords, cursor, result, count);
+        SLB_LAUNCH_CHECK("sample_rebase_kernel");
+    } else {
+        sample_commit_kernel<<<1, 1, 0, st>>>(cursor, result);
+        SLB_LAUNCH_CHECK("sample_commit_kernel");
+    }
     return SLB_OK;
+}
+
+int slb_sample_bounded(const uint32_t* blocks, int64_t nwords, int64_t* cursor, uint32_t rng,
+                       int64_t count, int64_t* out, void* workspace, size_t workspace_bytes,
+                       slb_stream_t stream) {
+    return sample_bounded_impl(const_cast<uint32_t*>(blocks), nwords, cursor, rng, count, out, workspace,
+                               workspace_bytes, false, stream);
+}
+
+int slb_sample_bounded_chain(uint32_t* blocks, int64_t nwords, int64_t* cursor, uint32_t rng,
+                             int64_t count, int64_t* out, void* workspace, size_t workspace_bytes,
+                             slb_stream_t stream) {
+    return sample_bounded_impl(blocks, nwords, cursor, rng, count, out, workspace, workspace_bytes, true, stream);
 }
 
 }  // extern "C"

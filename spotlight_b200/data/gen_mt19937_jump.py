@@ -10,7 +10,12 @@ output bit sequence and the table g_k = x^(624 * 2^k) mod phi for k = 0..KMAX
 by repeated squaring, and writes them as 624 little-endian uint32 words each
 (bit i of the polynomial = bit (i % 32) of word i // 32).
 
-Run:  python spotlight_b200/data/gen_mt19937_jump.py   (a few seconds)
+A second table serves the one-round generator (slb_mt19937_fill_direct): row r - 1 of
+``mt19937_jump_direct.npy`` is x^(624 * J0 * r) mod phi for r = 1..DIRECT_ROWS with
+J0 = 2^DIRECT_J0_LOG2 blocks, so CTA r reaches its start state r * J0 blocks ahead
+with a single polynomial evaluation instead of log2(r) doubling rounds.
+
+Run:  python spotlight_b200/data/gen_mt19937_jump.py   (under a minute)
 """
 
 import os
@@ -19,6 +24,8 @@ import numpy as np
 
 DEG = 19937
 KMAX = 26          # jumps up to 2^26 blocks = 4.2e10 words
+DIRECT_J0_LOG2 = 8     # fine stride of the direct table: 256 blocks
+DIRECT_ROWS = 255      # multiples 1..255 (256 fine slots per coarse slot)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -84,6 +91,18 @@ def gf2_mod(p, phi, deg):
     return p
 
 
+def gf2_mul(a, b):
+    """a(x) * b(x) over GF(2)."""
+    if a.bit_count() > b.bit_count():
+        a, b = b, a
+    out = 0
+    while a:
+        low = a & -a
+        out ^= b << (low.bit_length() - 1)
+        a ^= low
+    return out
+
+
 def main():
     words = mt_words(5489, 2 * DEG + 1000)
     bits = [w & 1 for w in words[1:2 * DEG + 600]]     # x[0]'s low 31 bits are not state
@@ -98,6 +117,16 @@ def main():
         table[k] = np.frombuffer(raw, dtype='<u4')
         g = gf2_mod(gf2_square(g), phi, DEG)
     np.save(os.path.join(HERE, 'mt19937_jump.npy'), table)
+    base = int.from_bytes(table[DIRECT_J0_LOG2].astype('<u4').tobytes(), 'little')    # x^(624 * J0)
+    direct = np.zeros((DIRECT_ROWS, 624), dtype=np.uint32)
+    g = base
+    for r in range(1, DIRECT_ROWS + 1):
+        direct[r - 1] = np.frombuffer(g.to_bytes(624 * 4, 'little'), dtype='<u4')
+        g = gf2_mod(gf2_mul(g, base), phi, DEG)
+    # the power-of-two multiples must agree with the squaring table
+    for k in range(DIRECT_J0_LOG2, DIRECT_J0_LOG2 + 8):
+        assert (direct[(1 << (k - DIRECT_J0_LOG2)) - 1] == table[k]).all(), k
+    np.save(os.path.join(HERE, 'mt19937_jump_direct.npy'), direct)
     print('phi weight', bin(phi).count('1'), 'table', table.shape)
 
 

@@ -217,7 +217,13 @@ class ImplicitFactorizationModel(object):
             users_dev, items_dev = users_dev.long(), items_dev.long()
         # _check_input (implicit.py:166-181) on the resident copy: same errors, no host pass
         if n:
-            self._check_input(int(users_dev.max()), int(items_dev.max()))
+            umax, imax, umin, imin = torch.stack([users_dev.max(), items_dev.max(), users_dev.min(),
+                                                  items_dev.min()]).tolist()        # one sync
+            self._check_input(int(umax), int(imax))
+            if umin < 0 or imin < 0:
+                # the reference fails inside the embedding lookup (IndexError); same outcome,
+                # raised before any kernel runs, on every route
+                raise IndexError('index out of range in self: negative user or item id')
 
         for epoch_num in range(self._n_iter):
             # shuffle(): same stream consumption as random_state.shuffle(arange(n))
@@ -278,20 +284,30 @@ class ImplicitFactorizationModel(object):
         # one buffer for the epoch's negatives (cached by the allocator across epochs);
         # sampler scratch sized once for the largest chunk (no cudaMalloc mid-epoch)
         negs_all = torch.empty(n * n_neg, dtype=torch.int64, device=dev)
+        # the block just handed out may still be read by work queued on the main stream
+        # (it was freed there); the sampler writes it on the side stream
+        side.wait_stream(main)
+        from spotlight_b200 import rng as _rng
         with torch.cuda.stream(side):
-            from spotlight_b200 import rng as _rng
             _rng.reserve(self._num_items, min(chunk, n) * n_neg, dev)
+            # the generator lives on the device for the whole epoch: the draws chain without
+            # a host round trip and finish() hands the state back once (spotlight_b200/rng.py)
+            stream = _rng.DeviceStream(self._random_state, dev)
         drawn = [0]
+        total = n * n_neg
 
         def draw(count):
             lo_v = drawn[0]
             drawn[0] += count * n_neg
             with torch.cuda.stream(side):
-                negs = sample_items(self._num_items, count * n_neg, random_state=self._random_state,
-                                    device=dev, out=negs_all[lo_v:drawn[0]])
+                negs = stream.draw(self._num_items, count * n_neg, out=negs_all[lo_v:drawn[0]])
                 ev = torch.cuda.Event()
                 ev.record(side)
-            if after_sampling is not None and drawn[0] == n * n_neg:
+                if after_sampling is not None and drawn[0] == total:
+                    # waits for the sampler only; the main stream still holds the previous
+                    # chunk's training steps
+                    stream.finish()
+            if after_sampling is not None and drawn[0] == total:
                 after_sampling()                # RandomState is final for this epoch
             return negs, ev
 
@@ -312,6 +328,8 @@ class ImplicitFactorizationModel(object):
             if lo < n:
                 cur = min(min(2 * cnt, chunk), n - lo)
                 nxt = draw(cur)
+        with torch.cuda.stream(side):
+            stream.finish()                     # no-op when the hook above already ran it
         host = torch.cat(parts).cpu().numpy().astype(np.float64)       # one sync per epoch
         ws = ops.workspace('mf%d_%d' % (self._num_users, self._num_items), 0, dev)
         if ops.workspace_error_flag(ws):

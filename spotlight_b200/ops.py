@@ -74,8 +74,13 @@ def workspace(kind: str, nbytes: int, device) -> Tensor:
 
 
 def workspace_error_flag(ws: Tensor) -> int:
-    """Device-side id-range error flag of an MF workspace (int32 word 4)."""
-    return int(ws[:32].view(torch.int32)[4].item())
+    """Device-side id-range error flag of an MF workspace (int32 word 4); reading clears
+    it, so one bad batch does not poison later calls that share the cached workspace."""
+    word = ws[:32].view(torch.int32)[4:5]
+    flag = int(word.item())
+    if flag:
+        word.zero_()
+    return flag
 
 
 def _seeds_array(seeds):

@@ -34,36 +34,74 @@ def _mask_for(r):
 
 _SCRATCH = {}
 _JUMP = {}
-_PARALLEL_MIN_BLOCKS = 2048     # >= 2 slices of 1024 blocks: one jump round (~0.35 ms) already pays
+_STATES = {}
+_PARALLEL_MIN_BLOCKS = 512      # >= 2 slices of 256 blocks: one jump round (~0.35 ms) already pays
+_J0_LOG2 = 8                    # fine stride of the direct jump table (data/gen_mt19937_jump.py)
+_SIGMA = 12.0                   # stream-length margin of a device draw (chained draws cannot re-draw)
+
+
+def _dev_key(dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
 
 
 def _jump_table(dev):
-    """Device copy of the jump polynomials (data/mt19937_jump.npy) + state scratch."""
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    """Device copies of the jump polynomials (data/mt19937_jump*.npy)."""
+    key = _dev_key(dev)
     if key not in _JUMP:
         import os
-        tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data',
-                                   'mt19937_jump.npy'))
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+        tab = np.load(os.path.join(here, 'mt19937_jump.npy'))
+        direct = np.load(os.path.join(here, 'mt19937_jump_direct.npy'))
         _JUMP[key] = (torch.from_numpy(tab.view(np.int32)).to(dev), int(tab.shape[0]),
-                      torch.empty(128 * _N, dtype=torch.int32, device=dev))
+                      torch.from_numpy(direct.view(np.int32)).to(dev), int(direct.shape[0]))
     return _JUMP[key]
+
+
+def _states(dev, slots):
+    """Jump-state scratch per (device, stream): the shuffle and the sampler may run on
+    different streams at the same time."""
+    key = (_dev_key(dev), torch.cuda.current_stream(dev).cuda_stream)
+    cur = _STATES.get(key)
+    if cur is None or cur.numel() < slots * _N:
+        cur = torch.empty(max(int(slots * 1.5), 512) * _N, dtype=torch.int32, device=dev)
+        _STATES[key] = cur
+    return cur
+
+
+def generate_blocks(blocks, nblocks, dev):
+    """Fill blocks[1..nblocks) from blocks[0] on the current stream (asynchronous)."""
+    lib = _lib.load()
+    if nblocks >= _PARALLEL_MIN_BLOCKS:
+        table, rows, direct, drows = _jump_table(dev)
+        slots = int(lib.slb_mt19937_direct_slots(nblocks, _J0_LOG2))
+        states = _states(dev, slots)
+        _lib.check(lib.slb_mt19937_fill_direct(_ptr(blocks), nblocks, _ptr(table), rows, _ptr(direct),
+                                               drows, _J0_LOG2, _ptr(states), states.numel() // _N,
+                                               _stream()), 'mt19937_fill_direct')
+    else:
+        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
 
 
 def _scratch(dev, nwords, ws_bytes):
     """Persistent (blocks, workspace, cursor) per device and stream: the sampler
     runs every epoch, and a fresh cudaMalloc would synchronise the device."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(dev).cuda_stream)
+    key = (_dev_key(dev), torch.cuda.current_stream(dev).cuda_stream)
     cur = _SCRATCH.get(key)
     if cur is None or cur[0].numel() < nwords or cur[1].numel() < ws_bytes:
         grow = 1.5 if cur is not None else 1.0
         cur = (torch.empty(int(nwords * grow), dtype=torch.int32, device=dev),
                torch.empty(int(ws_bytes * grow) + 4096, dtype=torch.uint8, device=dev),
-               torch.empty(2, dtype=torch.int64, device=dev),
+               torch.empty(4, dtype=torch.int64, device=dev),
                torch.empty(_N, dtype=torch.int32).pin_memory(),
-               torch.empty(2, dtype=torch.int64).pin_memory())
+               torch.empty(4, dtype=torch.int64).pin_memory())
         _SCRATCH[key] = cur
     return cur
+
+
+def _words_for(count, p_accept, pos=0):
+    """Stream words (whole blocks) that hold `count` accepted values with a _SIGMA margin."""
+    need = count / p_accept + _SIGMA * math.sqrt(count * (1 - p_accept)) / p_accept + 64
+    return (int(math.ceil((pos + need) / _N)) + 1) * _N
 
 
 def reserve(num_items, count, device):
@@ -73,10 +111,99 @@ def reserve(num_items, count, device):
         return
     lib = _lib.load()
     p_accept = (rng + 1) / float(_mask_for(rng) + 1)
-    want = min(int(count), _MAX_CHUNK)
-    need_words = want / p_accept + 8.0 * math.sqrt(want * (1 - p_accept)) / p_accept + 64
-    nwords = (int(math.ceil((_N + need_words) / _N)) + 1) * _N
-    _scratch(torch.device(device), nwords, lib.slb_sample_workspace_bytes(nwords))
+    nwords = _words_for(min(int(count), _MAX_CHUNK), p_accept, _N)
+    dev = torch.device(device)
+    _scratch(dev, nwords, lib.slb_sample_workspace_bytes(nwords))
+    if nwords // _N >= _PARALLEL_MIN_BLOCKS:
+        _jump_table(dev)
+        _states(dev, int(lib.slb_mt19937_direct_slots(nwords // _N, _J0_LOG2)))
+
+
+class DeviceStream(object):
+    """The model's ``RandomState`` taken over by the device for a run of draws.
+
+    ``draw`` enqueues a bit-exact ``randint(0, num_items, count)`` and leaves the
+    generator hand-over on the device (``slb_sample_bounded_chain``), so any number
+    of draws -- one per minibatch in the reference, implicit.py:256-259 -- chain on
+    the current stream without a host round trip.  ``finish`` is the single
+    synchronisation: it reads the (key, pos) pair back and ``set_state``s it on the
+    host ``RandomState``, which is then exactly where NumPy would have left it.
+    All calls must be made with the same current stream.
+    """
+
+    def __init__(self, random_state, device):
+        self.rs, self.dev = random_state, torch.device(device)
+        st = random_state.get_state()
+        if st[0] != 'MT19937':
+            raise ValueError('DeviceStream needs a legacy MT19937 RandomState')
+        self._gauss = (st[3], st[4])
+        self._blocks = None
+        self._key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        self._pos = int(st[2])
+        self._open = False
+        self._drawn = 0
+
+    def _ensure(self, nwords, ws_bytes):
+        blocks, ws, cursor, pin_key, pin_cur = _scratch(self.dev, nwords, ws_bytes)
+        if not self._open:
+            pin_key.copy_(torch.from_numpy(self._key.view(np.int32)))
+            blocks[:_N].copy_(pin_key, non_blocking=True)
+            pin_cur[0], pin_cur[1], pin_cur[2], pin_cur[3] = self._pos, 0, 0, 0
+            cursor.copy_(pin_cur, non_blocking=True)
+            self._open = True
+        elif blocks is not self._blocks:            # scratch grew: carry the device state over
+            blocks[:_N].copy_(self._blocks[:_N])
+            cursor.copy_(self._cursor)
+        self._blocks, self._ws, self._cursor, self._pin_key, self._pin_cur = blocks, ws, cursor, pin_key, pin_cur
+
+    def draw(self, num_items, count, out=None):
+        """``randint(0, num_items, count, dtype=int64)`` into ``out`` (asynchronous)."""
+        count = int(count)
+        if out is None:
+            out = torch.empty(count, dtype=torch.int64, device=self.dev)
+        out = out.reshape(-1)
+        if out.numel() != count or out.dtype != torch.int64 or not out.is_contiguous():
+            raise ValueError('DeviceStream.draw: out must be a contiguous int64 tensor of %d' % count)
+        rng = int(num_items) - 1
+        if rng < 0:
+            raise ValueError('num_items must be positive')
+        if count == 0:
+            return out
+        if rng == 0:                       # numpy consumes no randomness for a 1-value range
+            return out.zero_()
+        if rng >= 0xFFFFFFFF:
+            raise ValueError('num_items must be < 2**32')
+        lib = _lib.load()
+        p_accept = (rng + 1) / float(_mask_for(rng) + 1)
+        done = 0
+        while done < count:
+            want = min(count - done, _MAX_CHUNK)
+            nwords = _words_for(want, p_accept, _N)       # the hand-over position is <= 624
+            self._ensure(nwords, lib.slb_sample_workspace_bytes(nwords))
+            generate_blocks(self._blocks, nwords // _N, self.dev)
+            rc = lib.slb_sample_bounded_chain(_ptr(self._blocks), nwords, _ptr(self._cursor),
+                                              ctypes.c_uint32(rng), want, _ptr(out[done:done + want]),
+                                              _ptr(self._ws), self._ws.numel(), _stream())
+            _lib.check(rc, 'sample_bounded_chain')
+            done += want
+            self._drawn += want
+        return out
+
+    def finish(self):
+        """Synchronise, hand the generator back to the host ``RandomState``."""
+        if not self._open:
+            return
+        self._pin_key.copy_(self._blocks[:_N], non_blocking=True)
+        self._pin_cur.copy_(self._cursor, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        pos, _, short, produced = (int(v) for v in self._pin_cur.tolist())
+        key = self._pin_key.numpy().view(np.uint32).copy()
+        self._open = False
+        if short or produced != self._drawn:
+            raise RuntimeError('device sampler ran out of stream words (a %g-sigma event): %d of %d '
+                               'values drawn' % (_SIGMA, produced, self._drawn))
+        self.rs.set_state(('MT19937', key, pos, self._gauss[0], self._gauss[1]))
+        self._key, self._pos, self._drawn = key, pos, 0
 
 
 def sample_items_device(num_items, shape, random_state, device, out=None):
@@ -87,62 +214,10 @@ def sample_items_device(num_items, shape, random_state, device, out=None):
     """
     shape = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
     count = int(np.prod(shape)) if len(shape) else 1
-    dev = torch.device(device)
-    if out is None:
-        out = torch.empty(count, dtype=torch.int64, device=dev)
-    else:
-        out = out.reshape(-1)
-        if out.numel() != count or out.dtype != torch.int64 or not out.is_contiguous():
-            raise ValueError('sample_items_device: out must be a contiguous int64 tensor of %d' % count)
-    rng = int(num_items) - 1
-    if rng < 0:
-        raise ValueError('num_items must be positive')
-    if count == 0:
-        return out.reshape(shape)
-    if rng == 0:                       # numpy consumes no randomness for a 1-value range
-        return out.zero_().reshape(shape)
-    if rng >= 0xFFFFFFFF:
-        raise ValueError('num_items must be < 2**32')
-    lib = _lib.load()
-    p_accept = (rng + 1) / float(_mask_for(rng) + 1)
-
-    st = random_state.get_state()
-    key = np.ascontiguousarray(st[1], dtype=np.uint32)
-    pos = int(st[2])
-    done = 0
-    while done < count:
-        want = min(count - done, _MAX_CHUNK)
-        # words needed ~ want / p  (+ 8 sigma), plus the unread tail of block 0
-        need_words = want / p_accept + 8.0 * math.sqrt(want * (1 - p_accept)) / p_accept + 64
-        nblocks = int(math.ceil((pos + need_words) / _N)) + 1
-        nwords = nblocks * _N
-        blocks, ws, cursor, pin_key, pin_cur = _scratch(dev, nwords, lib.slb_sample_workspace_bytes(nwords))
-        pin_key.copy_(torch.from_numpy(key.view(np.int32)))
-        blocks[:_N].copy_(pin_key, non_blocking=True)
-        pin_cur[0], pin_cur[1] = pos, 0
-        cursor.copy_(pin_cur, non_blocking=True)
-        if nblocks >= _PARALLEL_MIN_BLOCKS:
-            table, rows, states = _jump_table(dev)
-            _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
-                                                     _ptr(states), _stream()), 'mt19937_fill_parallel')
-        else:
-            _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
-        chunk = out[done:done + want]
-        rc = lib.slb_sample_bounded(_ptr(blocks), nwords, _ptr(cursor), ctypes.c_uint32(rng), want,
-                                    _ptr(chunk), _ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, 'sample_bounded')
-        end, produced = (int(v) for v in cursor.tolist())       # sync: once per chunk
-        done += produced
-        # hand the state over: block containing the next unread word
-        if end >= nwords:                       # stream exhausted (rare: 8-sigma margin)
-            blk, pos = nblocks - 1, _N
-        elif end % _N == 0 and end > 0:         # numpy leaves pos = 624 on a block boundary
-            blk, pos = end // _N - 1, _N
-        else:
-            blk, pos = end // _N, end % _N
-        key = blocks[blk * _N:(blk + 1) * _N].cpu().numpy().view(np.uint32).copy()
-    random_state.set_state(('MT19937', key, pos, 0, 0.0))
-    return out.reshape(shape)
+    stream = DeviceStream(random_state, device)
+    res = stream.draw(num_items, count, out)
+    stream.finish()
+    return res.reshape(shape)
 
 
 _GAMMA = 0.5772156649015329
@@ -212,12 +287,7 @@ def shuffle_begin(n, random_state, device, rounds=40, margin=8.0):
     ws, cursor = cur
     pin_key.copy_(torch.from_numpy(key.view(np.int32)))
     blocks[:_N].copy_(pin_key, non_blocking=True)
-    if nblocks >= _PARALLEL_MIN_BLOCKS:
-        table, rows, states = _jump_table(dev)
-        _lib.check(lib.slb_mt19937_fill_parallel(_ptr(blocks), nblocks, _ptr(table), rows,
-                                                 _ptr(states), _stream()), 'mt19937_fill_parallel')
-    else:
-        _lib.check(lib.slb_mt19937_fill(_ptr(blocks), nblocks, _stream()), 'mt19937_fill')
+    generate_blocks(blocks, nblocks, dev)
     order = torch.empty(n, dtype=torch.int64, device=dev)
     h.update(st=st, pos=pos, nwords=nwords, blocks=blocks, ws=ws, cursor=cursor, order=order)
     _shuffle_launch(h, 0)

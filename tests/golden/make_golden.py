@@ -286,6 +286,9 @@ if __name__ == '__main__':
              cnn_kwargs=dict(kernel_width=3, dilation=1, num_layers=1))
     seq_case('cnn_bpr_l2_relu', 'bpr', 'cnn', num_items=61, dim=16, batch=10, S=11,
              cnn_kwargs=dict(kernel_width=3, dilation=(1, 2), num_layers=2, nonlinearity='relu'))
+    # D = 128: the tcgen05 conv path of the product (csrc/seq_tc.cuh) against the live reference
+    seq_case('cnn_pointwise_d128', 'pointwise', 'cnn', num_items=61, dim=128, batch=10, S=25,
+             cnn_kwargs=dict(kernel_width=3, dilation=1, num_layers=1))
     seq_case('cnn_adaptive_k5_nores', 'adaptive_hinge', 'cnn', num_items=61, dim=16, batch=6,
              S=12, cnn_kwargs=dict(kernel_width=5, dilation=(2, 3), num_layers=2,
                                    residual_connections=False))

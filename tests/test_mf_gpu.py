@@ -29,6 +29,15 @@ def t(x):
     return torch.from_numpy(np.ascontiguousarray(x)).to(dev())
 
 
+def assert_close_dev(actual, expected, rtol=1e-5, atol=0.0, what=''):
+    """conftest.assert_close for multi-GB tensors: same criterion, evaluated on the device."""
+    assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    scale = expected.abs().max().item()
+    err = (actual - expected).abs().max().item()
+    tol = rtol * scale + atol
+    assert err <= tol, '%s: max err %.3e > tol %.3e (scale %.3e)' % (what, err, tol, scale)
+
+
 # ------------------------------------------------------------------ sampler
 
 @pytest.mark.parametrize('num_items,shape', [(100000, 70000), (1683, (5, 77)), (1000000, 1234),
@@ -63,10 +72,19 @@ def test_parallel_generator_matches_sequential_and_numpy():
         a[:624] = torch.from_numpy(key.view(np.int32)).to(dev())
         b[:624] = a[:624]
         _lib.check(lib.slb_mt19937_fill(_ptr(a), nblocks, _stream()), 'seq')
-        table, rows, states = rng._jump_table(dev())
+        table, rows, direct, drows = rng._jump_table(dev())
+        states = rng._states(dev(), 4096)
         _lib.check(lib.slb_mt19937_fill_parallel(_ptr(b), nblocks, _ptr(table), rows, _ptr(states),
                                                  _stream()), 'par')
         assert torch.equal(a, b), nblocks
+        # one-round generator: precomputed multiples of 256 blocks (+ doubling over the coarse
+        # slots once the stream exceeds 256 fine slots: 70001 blocks = 274 slots)
+        c = torch.zeros_like(a)
+        c[:624] = a[:624]
+        _lib.check(lib.slb_mt19937_fill_direct(_ptr(c), nblocks, _ptr(table), rows, _ptr(direct), drows,
+                                               rng._J0_LOG2, _ptr(states), states.numel() // 624,
+                                               _stream()), 'direct')
+        assert torch.equal(a, c), nblocks
     from spotlight_b200.sampling import sample_items
     r1, r2 = np.random.RandomState(5), np.random.RandomState(5)
     want = r1.randint(0, 100000, 30_000_000, dtype=np.int64)
@@ -74,6 +92,34 @@ def test_parallel_generator_matches_sequential_and_numpy():
     assert (got.cpu().numpy() == want).all()
     s1, s2 = r1.get_state(), r2.get_state()
     assert (s1[1] == s2[1]).all() and s1[2] == s2[2]
+
+
+def test_chained_draws_one_sync():
+    """DeviceStream: many draws (one per minibatch in the reference, implicit.py:256-259)
+    chained on the device, one hand-back at the end -- bit-exact values and final state."""
+    from spotlight_b200.rng import DeviceStream
+    a, b = np.random.RandomState(77), np.random.RandomState(77)
+    a.randint(0, 10, 300); b.randint(0, 10, 300)
+    plan = [(100000, 524288), (100000, 1), (1683, 4097), (100000, 3_000_000), (50000000, 70000),
+            (1, 9), (100000, 624), (1000000, 2_500_000)]
+    want = [a.randint(0, n, c, dtype=np.int64) for n, c in plan]
+    with torch.cuda.stream(torch.cuda.Stream()):
+        st = DeviceStream(b, dev())
+        got = [st.draw(n, c) for n, c in plan]
+        st.finish()
+    for w, g, pc in zip(want, got, plan):
+        assert (g.cpu().numpy() == w).all(), pc
+    sa, sb = a.get_state(), b.get_state()
+    assert (sa[1] == sb[1]).all() and sa[2] == sb[2]
+    assert (a.randint(0, 1000, 50) == b.randint(0, 1000, 50)).all()
+    # gaussian cache of the RandomState survives the take-over (ADVICE r1)
+    c = np.random.RandomState(3)
+    c.standard_normal(1)
+    has, val = c.get_state()[3:5]
+    st = DeviceStream(c, dev())
+    st.draw(1000, 10)
+    st.finish()
+    assert c.get_state()[3:5] == (has, val)
 
 
 def test_sampler_golden_stream():
@@ -242,6 +288,96 @@ def test_fused_step_full_size_properties():
     # conservation: bpr gives gp + gn = 0 per interaction
     assert abs(dbi.double().sum().item()) < 1e-6
     assert torch.count_nonzero(dbu).item() == 0 or dbu.abs().max().item() < 1e-9
+
+
+def test_fused_step_config3_size():
+    """BASELINE config 3 shape on one GPU (10M users x 1M items x 128, adaptive hinge with
+    n = 5 negatives, B = 65536): loss, scores and all gradients vs an fp32 ATen restatement
+    of the reference step *including* its user/negative pairing (implicit.py:266-275: flat
+    negative f is scored with users[f // n] and read as element (f // B, f % B))."""
+    from spotlight_b200 import ops
+    torch.manual_seed(3)
+    U, I, D, B, n = 10_000_000, 1_000_000, 128, 65536, 5
+    d = dev()
+    Wu = torch.randn(U, D, device=d) / D
+    Wi = torch.randn(I, D, device=d) / D
+    bu = torch.randn(U, 1, device=d) * 0.01
+    bi = torch.randn(I, 1, device=d) * 0.01
+    users = torch.randint(0, U, (B,), device=d)
+    items = torch.randint(0, I, (B,), device=d)
+    negs = torch.randint(0, I, (B * n,), device=d)
+    loss, pos, neg, dWu, dWi, dbu, dbi = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 3, n, True)
+    u_rep = users.view(B, 1).expand(B, n).reshape(B * n)
+    p = (Wu[users] * Wi[items]).sum(1) + bu[users, 0] + bi[items, 0]
+    s = (Wu[u_rep] * Wi[negs]).sum(1) + bu[u_rep, 0] + bi[negs, 0]
+    hardest, k = s.view(n, B).max(0)
+    z = hardest - p + 1.0
+    assert_close(pos.cpu().numpy(), p.cpu().numpy(), 1e-5, what='pos')
+    assert_close(neg.cpu().numpy(), s.cpu().numpy(), 1e-5, what='neg')
+    assert_close(loss.item(), z.clamp(min=0).mean().item(), 1e-5, what='loss')
+    act = (z >= 0).float() / B
+    f = k * B + torch.arange(B, device=d)                   # flat index of the arg-max negative
+    rWu = torch.zeros_like(Wu).index_add_(0, users, -act[:, None] * Wi[items])
+    rWu.index_add_(0, u_rep[f], act[:, None] * Wi[negs[f]])
+    assert_close_dev(dWu, rWu, 1e-5, what='dWu')
+    del rWu
+    rWi = torch.zeros_like(Wi).index_add_(0, items, -act[:, None] * Wu[users])
+    rWi.index_add_(0, negs[f], act[:, None] * Wu[u_rep[f]])
+    assert_close_dev(dWi, rWi, 1e-5, what='dWi')
+    rbu = torch.zeros(U, device=d).index_add_(0, users, -act).index_add_(0, u_rep[f], act)
+    rbi = torch.zeros(I, device=d).index_add_(0, items, -act).index_add_(0, negs[f], act)
+    assert_close_dev(dbu.reshape(-1), rbu, 1e-5, atol=1e-9, what='dbu')
+    assert_close_dev(dbi.reshape(-1), rbi, 1e-5, atol=1e-9, what='dbi')
+    o2 = ops.mf_train_step(Wu, Wi, bu, bi, users, items, negs, 3, n, False)
+    assert torch.equal(o2[3], dWu) and torch.equal(o2[4], dWi), 'not bit-reproducible'
+
+
+def test_fused_bloom_step_config4_size():
+    """BASELINE config 4 shape on one GPU (BloomEmbedding 50M items -> 1M hashed rows, D = 64,
+    H = 4, hinge, plain 1M-user table, item bias unhashed 50M x 1, B = 65536): the fused
+    hashed step vs an fp32 ATen restatement built on the oracle's murmur rows
+    (layers.py:178-204, 240-241)."""
+    from oracle.murmur import bloom_rows
+    from spotlight_b200 import ops
+    from spotlight_b200.layers import SEEDS
+    torch.manual_seed(4)
+    U, N, M, D, H, B = 1_000_000, 50_000_000, 1_000_000, 64, 4, 65536
+    d = dev()
+    Wu = torch.randn(U, D, device=d) / D
+    Wi = torch.randn(M, D, device=d) / D
+    Wi[0] = 0                                                # padding row of the hashed table
+    bu = torch.randn(U, 1, device=d) * 0.01
+    bi = torch.randn(N, 1, device=d) * 0.01
+    rs = np.random.RandomState(44)
+    users = t(rs.randint(0, U, B).astype(np.int64))
+    items_h = rs.randint(1, N, B).astype(np.int64)
+    negs_h = rs.randint(0, N, B).astype(np.int64)
+    negs_h[:3] = 0                                           # the padding id among the negatives
+    items, negs = t(items_h), t(negs_h)
+    loss, pos, neg, dWu, dWi, dbu, dbi = ops.mf_bloom_train_step(Wu, Wi, bu, bi, users, items, negs, 2, 1,
+                                                                [], SEEDS[:H], -1, 0, True)
+    ri, rj = t(bloom_rows(items_h, H, M)), t(bloom_rows(negs_h, H, M))      # (B, H) int64, oracle murmur
+    assert int(rj[:3].abs().sum()) == 0
+    u = Wu[users]
+    qi, qj = Wi[ri].sum(1), Wi[rj].sum(1)
+    p = (u * qi).sum(1) + bu[users, 0] + bi[items, 0]
+    ng = (u * qj).sum(1) + bu[users, 0] + bi[negs, 0]
+    z = ng - p + 1.0
+    assert_close(pos.cpu().numpy(), p.cpu().numpy(), 1e-5, what='pos')
+    assert_close(neg.cpu().numpy(), ng.cpu().numpy(), 1e-5, what='neg')
+    assert_close(loss.item(), z.clamp(min=0).mean().item(), 1e-5, what='loss')
+    act = (z >= 0).float() / B
+    rWu = torch.zeros_like(Wu).index_add_(0, users, act[:, None] * (qj - qi))
+    gu = act[:, None] * u
+    rWi = torch.zeros_like(Wi)
+    for k in range(H):
+        rWi.index_add_(0, ri[:, k], -gu).index_add_(0, rj[:, k], gu)
+    rWi[0] = 0                                               # frozen padding row
+    assert_close_dev(dWu, rWu, 1e-5, what='dWu')
+    assert_close_dev(dWi, rWi, 1e-5, what='dWi')
+    rbi = torch.zeros(N, device=d).index_add_(0, items, -act).index_add_(0, negs, act)
+    assert_close_dev(dbi.reshape(-1), rbi, 1e-5, atol=1e-9, what='dbi')
+    assert dbu.abs().max().item() < 1e-9                     # hinge: gp + gn = 0 per interaction
 
 
 # -------------------------------------------------------- scores / embedding
