@@ -314,21 +314,31 @@ def kernel_breakdown(model, users, items, a, steps):
     Wu, Wi = net.user_embeddings.weight, net.item_embeddings.weight
     bu, bi = net.user_biases.weight, net.item_biases.weight
     negs = sample_items(a.items, steps * B, random_state=np.random.RandomState(1), device=dev)
-    names = ['mf_fwd', 'seg_scan', 'mf_fill', 'mf_bwd', 'mf_apply']
+    from spotlight_b200.factorization import implicit as _impl
+    fused_need = lib.slb_mf_fused_workspace_bytes(B, a.users, a.items, a.dim) if _impl.PLANNED_STEP else 0
+    if fused_need:      # planned step: integer plan, user kernel (forward + dU + update), item kernel
+        names, bits = ['plan', 'mf_user', 'mf_item'], [1, 2, 4]
+    else:
+        names, bits = ['mf_fwd', 'seg_scan', 'mf_fill', 'mf_bwd', 'mf_apply'], [1, 2, 4, 8, 16]
     tot = dict.fromkeys(names, 0.0)
     with torch.no_grad():
         st = ops.mf_step_args(Wu, Wi, bu, bi, users[:B], items[:B], negs[:B], a.loss, 1, batch=B)
-        rows = lib.slb_mf_compact_rows(B, 1, st.loss, 0)
-        bufs = dict(urows=torch.empty(rows, dtype=torch.int64, device=dev),
-                    irows=torch.empty(rows, dtype=torch.int64, device=dev),
-                    gWu=torch.empty((rows, a.dim), device=dev), gWi=torch.empty((rows, a.dim), device=dev),
-                    gbu=torch.empty(rows, device=dev), gbi=torch.empty(rows, device=dev),
-                    counts=torch.zeros(2, dtype=torch.int32, device=dev),
-                    loss=torch.empty(1, device=dev))
         st.grad_mode = _lib.GRAD_COMPACT
-        st.urows, st.gWu, st.gbu = bufs['urows'].data_ptr(), bufs['gWu'].data_ptr(), bufs['gbu'].data_ptr()
-        st.irows, st.gWi, st.gbi = bufs['irows'].data_ptr(), bufs['gWi'].data_ptr(), bufs['gbi'].data_ptr()
-        st.compact_counts, st.loss_out = bufs['counts'].data_ptr(), bufs['loss'].data_ptr()
+        bufs = dict(loss=torch.empty(1, device=dev))
+        if fused_need:
+            bufs['fws'] = ops.workspace('mfv2_%d_%d_%d_%d' % (a.users, a.items, a.dim, B), fused_need, dev)
+            st.fused_workspace, st.fused_workspace_bytes = bufs['fws'].data_ptr(), bufs['fws'].numel()
+        else:
+            rows = lib.slb_mf_compact_rows(B, 1, st.loss, 0)
+            bufs.update(urows=torch.empty(rows, dtype=torch.int64, device=dev),
+                        irows=torch.empty(rows, dtype=torch.int64, device=dev),
+                        gWu=torch.empty((rows, a.dim), device=dev), gWi=torch.empty((rows, a.dim), device=dev),
+                        gbu=torch.empty(rows, device=dev), gbi=torch.empty(rows, device=dev),
+                        counts=torch.zeros(2, dtype=torch.int32, device=dev))
+            st.urows, st.gWu, st.gbu = bufs['urows'].data_ptr(), bufs['gWu'].data_ptr(), bufs['gbu'].data_ptr()
+            st.irows, st.gWi, st.gbi = bufs['irows'].data_ptr(), bufs['gWi'].data_ptr(), bufs['gbi'].data_ptr()
+            st.compact_counts = bufs['counts'].data_ptr()
+        st.loss_out = bufs['loss'].data_ptr()
         hp = opt.fused_hparams()
         st.opt, st.lr, st.weight_decay, st.eps = opt.fused_kind, hp['lr'], hp['weight_decay'], hp['eps']
         states = [opt.fused_state(p) for p in (Wu, Wi, bu, bi)]
@@ -336,15 +346,15 @@ def kernel_breakdown(model, users, items, a, steps):
         need = lib.slb_mf_step_workspace_bytes(B, 1, st.loss, a.users, a.items)
         ws = ops.workspace('mf%d_%d' % (a.users, a.items), need, dev)
         st.workspace, st.workspace_bytes = ws.data_ptr(), ws.numel()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         stream = ops._stream()
         for k in range(steps):
             st.users = users[k * B:].data_ptr()
             st.items = items[k * B:].data_ptr()
             st.negs = negs[k * B:].data_ptr()
             evs[0].record()
-            for i in range(5):
-                _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(st), 1 << i, stream), 'phase')
+            for i, bit in enumerate(bits):
+                _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(st), bit, stream), 'phase')
                 evs[i + 1].record()
             torch.cuda.synchronize()
             for i, nm in enumerate(names):
@@ -382,55 +392,57 @@ def sharded_e2e(a, rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         calls.append(n_all / float(t.item()))
     e2e = {'value': calls[1], 'unit': UNIT, 'first_call_value': calls[0],
-           'h2d_bytes_per_step': 8 * world * B, 'd2h_bytes_per_step': 4,
+           'h2d_bytes_per_step': 8 * B, 'd2h_bytes_per_step': 4,      # per rank: 1/world of the global minibatch's two int32 ids
            'note': 'ShardedImplicitFactorizationModel.fit(Interactions) on every rank with the same '
-                   'page-locked host int32 ids: H2D, range check, the global bit-exact '
-                   'RandomState.shuffle permutation and the global negative stream computed on every '
-                   'rank (single-process minibatch membership), owner routing, K sharded steps of '
-                   'global batch world*B, loss read-back; wall clock, max over ranks, second of two calls'}
+                   'page-locked host int32 ids: H2D of 1/world of the ids per rank + NVLink all-gather, '
+                   'range check, the global bit-exact RandomState.shuffle permutation and the global '
+                   'negative stream computed on every rank (single-process minibatch membership), owner '
+                   'routing, K sharded steps of global batch world*B, loss read-back; wall clock, max '
+                   'over ranks, second of two calls'}
     return e2e
 
 
 def main_sharded(a, rank, world, local):
-    """N > 1: item rows range-sharded over the ranks, users owner-routed, NCCL
-    all-to-all of requests / rows / gradient rows (spotlight_b200/sharded.py).
-    Weak scaling: every rank processes `batch` interactions per step."""
+    """N > 1: item rows range-sharded over the ranks, users owner-routed, NCCL exchange
+    (spotlight_b200/sharded.py).  Weak scaling: the global minibatch is world * batch.
+
+    `value` times ShardedImplicitFactorizationModel's own epoch loop on device-resident
+    (already shuffled) GLOBAL ids -- the global negative stream (device MT19937, chunked on a
+    side stream), the owner partition of every minibatch, the item-row exchange, the fused
+    local step and the owners' updates are all inside the timed region.
+    """
     import torch
     import torch.distributed as dist
-    from spotlight_b200.sampling import sample_items
-    from spotlight_b200.sharded import GpuBackend, ShardedMF, ShardPlan, ShardState
+    from spotlight_b200.sharded import ShardedImplicitFactorizationModel
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    B, K, W = a.batch, a.steps, a.warmup
-    plan = ShardPlan(a.users, a.items, world)
-    torch.manual_seed(100 + rank)
-    st = ShardState(plan, rank, a.dim, dev, lr=a.lr)
-    model = ShardedMF(plan, st, rank, GpuBackend(dev), cache_capacity=min(2 * B, a.items))
-    ulo, uhi = plan.user_range(rank)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    n = (K + W) * B
-    users = torch.randint(ulo, uhi, (n,), device=dev, generator=g)
-    items = torch.randint(0, a.items, (n,), device=dev, generator=g)
-    negs = sample_items(a.items, n, random_state=np.random.RandomState(99 + rank), device=dev)
-
-    def run(lo, steps):
-        last = None
-        for k in range(steps):
-            s = slice((lo + k) * B, (lo + k + 1) * B)
-            last = model.step(users[s], items[s], negs[s], a.loss, world * B, a.exchange)
-        return last
-
     sampler = ClockSampler(local).start() if rank == 0 else None
-    run(0, W)
+    B, K, W = a.batch, a.steps, a.warmup
+    gB = world * B
+    fm = ShardedImplicitFactorizationModel(a.users, a.items, rank, world, dev, loss=a.loss,
+                                           embedding_dim=a.dim, n_iter=1, batch_size=gB,
+                                           learning_rate=a.lr, random_state=np.random.RandomState(5),
+                                           exchange=a.exchange)
+    g = torch.Generator(device=dev).manual_seed(1234)           # same global ids on every rank
+    n = (K + W) * gB
+    users = torch.randint(0, a.users, (n,), device=dev, generator=g)
+    items = torch.randint(0, a.items, (n,), device=dev, generator=g)
+    chk = torch.stack([users.sum(), items.sum()]).double()
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_, hi_), 'ranks generated different global ids'
+
+    fm._run_epoch_device(users[:W * gB], items[:W * gB])        # W warm-up steps, same code path
     dist.barrier()
     torch.cuda.synchronize()
     if sampler:
         sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    model.stats = {'rows_requested': 0, 'bytes_a2a': 0}
+    fm.mf.stats = {'rows_requested': 0, 'bytes_a2a': 0}
     e0.record()
-    last = run(W, K)
+    last = fm._run_epoch_device(users[W * gB:], items[W * gB:])  # exactly K global steps
     e1.record()
     dist.barrier()
     torch.cuda.synchronize()
@@ -443,9 +455,9 @@ def main_sharded(a, rank, world, local):
 
     # ---- end to end through the public multi-GPU API (host ids) ---------
     e2e = None
-    stats = dict(model.stats)
+    stats = dict(fm.mf.stats)
     if not a.no_e2e:
-        del users, items, negs, model, st
+        del users, items, fm
         torch.cuda.empty_cache()
         try:
             e2e = sharded_e2e(a, rank, world, dev)
@@ -459,16 +471,22 @@ def main_sharded(a, rank, world, local):
                               % world + ('whole-shard NCCL all-gather / reduce-scatter per step (2B >= '
                                          'num_items: every row is needed by every rank)' if dense else
                                          'NCCL all-to-all of requests / rows / gradient rows'))
-        cfg['negatives'] = 'device MT19937 per rank (seeded per rank), pre-drawn'
+        cfg['batch'] = gB
+        cfg['batch_per_gpu'] = B
+        cfg['negatives'] = ('one global device MT19937 stream (numpy-bit-exact), drawn inside the timed '
+                            'region on every rank, chunked on a side stream')
+        cfg['timed_region'] = ('ShardedImplicitFactorizationModel._run_epoch_device on device-resident '
+                               'shuffled global ids: sampler + owner partition + exchange + steps')
         a2a_gb = stats['bytes_a2a'] / 1e9
         line = {'metric': METRIC, 'value': world * K * B / (ms * 1e-3), 'unit': UNIT,
                 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic', 'config': cfg, 'epoch_loss': float(last), 'clocks': clocks,
-                'e2e': e2e, 'gpu_launches': K * 30,
-                'nvlink': {'all_to_all_gbytes_per_rank': a2a_gb,
+                'e2e': e2e, 'gpu_launches': K * 20,
+                'nvlink': {'exchange_gbytes_per_rank': a2a_gb,
                            'achieved_gbs_per_rank': a2a_gb / (ms * 1e-3),
-                           'rows_requested_per_step': stats['rows_requested'] / K},
+                           'rows_requested_per_step': stats['rows_requested'] / K,
+                           'source': 'bytes counted from the tensors handed to NCCL / timed region'},
                 'roofline': None, 'cpu_baseline': None}
         print(json.dumps(line))
     dist.destroy_process_group()
@@ -569,26 +587,38 @@ def main_ours(a):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     R = 4 * a.dim
-    alg = {'mf_fwd': 3 * R + 60, 'mf_bwd': 7 * R + 84}        # bytes / interaction, DESIGN.md
+    if 'mf_user' in kb:     # planned step: bytes / interaction, rows counted per use
+        # mf_user: reads U, Q+, Q- rows + 3 biases + one 16-byte plan record; writes the updated U row + 2 g
+        # mf_item: reads the 2 stashed user rows + 2 x (8-byte record + g); writes the 2 updated item rows
+        alg = {'mf_user': 4 * R + 36, 'mf_item': 4 * R + 32}
+        traffic_file = 'traffic_r02.json'
+    else:
+        alg = {'mf_fwd': 3 * R + 60, 'mf_bwd': 7 * R + 84}
+        traffic_file = 'traffic_r01j.json'
     dom = max(alg, key=lambda k: kb[k])
     achieved = alg[dom] * B / (kb[dom] * 1e-3) / 1e9
     step_ms = sum(kb.values())
     traffic = None
     try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01j.json')))
+        tr = json.load(open(os.path.join(ROOT, 'profiles', traffic_file)))
         if tr['batch'] == B and tr['dim'] == a.dim:
             traffic = tr['dram_bytes_per_launch'].get(dom)
     except (OSError, ValueError, KeyError):
         pass
+    step_bytes = (6 * R + 40) * B
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic,
                 'algorithmic_bytes_per_launch': alg[dom] * B,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650',
                 'algorithmic_bytes_per_interaction': alg[dom],
                 'kernel_ms': kb,
+                'per_kernel_frac': {k: alg[k] * B / (kb[k] * 1e-3) / 1e9 / peak for k in alg},
+                # SURVEY section 8(d)'s figure for the whole step (6R + 40 per interaction) against the
+                # sum of the kernels timed one by one, and against the timed K-step region itself
                 'step_algorithmic': {'bytes_per_interaction': 6 * R + 40,
-                                     'achieved_gbs': (6 * R + 40) * B / (step_ms * 1e-3) / 1e9,
-                                     'frac': (6 * R + 40) * B / (step_ms * 1e-3) / 1e9 / peak}}
+                                     'achieved_gbs': step_bytes / (step_ms * 1e-3) / 1e9,
+                                     'frac': step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                                     'frac_of_timed_region': step_bytes / (ms / K * 1e-3) / 1e9 / peak}}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
@@ -596,11 +626,12 @@ def main_ours(a):
         cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
     n_chunks = 7 + max(0, (K - 127 + 63) // 64)      # sampler chunks: 1,2,4,..,64 batches
+    per_step = 10 if 'mf_user' in kb else 10         # planned: 6 plan + 2 user + 2 item; first generation: 10
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(a, world), 'epoch_loss': epoch_loss,
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': K * 10 + n_chunks * 12,     # 10 kernels per step + sampler (jump rounds, fill, 4 compaction)
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': K * per_step + n_chunks * 6,     # kernels per step + sampler (jump round, fill, 4 compaction)
             'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line))
     if world > 1:

@@ -30,8 +30,8 @@ EXPORTS = (
     'slb_shuffle_workspace_bytes', 'slb_shuffle_order', 'slb_permute_ids',
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
-    'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_compact_rows',
-    'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch',
+    'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
+    'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events',
     'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
     'slb_unique_workspace_bytes', 'slb_unique_bucket',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
@@ -56,6 +56,7 @@ class MfStepArgs(ctypes.Structure):
         ('state_Wu', c_vp), ('state_Wi', c_vp), ('state_bu', c_vp), ('state_bi', c_vp),
         ('norm_batch', c_i64), ('opt_users_only', c_i32),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
+        ('fused_workspace', c_vp), ('fused_workspace_bytes', c_sz), ('plan_stream', c_vp),
     ]
 
 
@@ -125,6 +126,8 @@ def _declare(lib):
                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
     lib.slb_mf_step_workspace_bytes.argtypes = [c_i64, c_i32, c_i32, c_i64, c_i64]
     lib.slb_mf_step_workspace_bytes.restype = c_sz
+    lib.slb_mf_fused_workspace_bytes.argtypes = [c_i64, c_i64, c_i64, c_i32]
+    lib.slb_mf_fused_workspace_bytes.restype = c_sz
     lib.slb_mf_compact_rows.argtypes = [c_i64, c_i32, c_i32, c_i32]
     lib.slb_mf_compact_rows.restype = c_i64
     lib.slb_mf_train_step.argtypes = [P(MfStepArgs), c_vp]
@@ -133,6 +136,7 @@ def _declare(lib):
     lib.slb_mf_bloom_workspace_bytes.restype = c_sz
     lib.slb_mf_bloom_train_step.argtypes = [P(MfBloomArgs), c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
+    lib.slb_mf_fit_epoch_events.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32]
     lib.slb_unique_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_unique_workspace_bytes.restype = c_sz
     lib.slb_unique_bucket.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]

@@ -783,6 +783,10 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
     }
 }
 
+constexpr int MF_MAX_GRID = 148 * 16;
+
+#include "mf_v2.cuh"
+
 template <int LPR>
 __global__ void __launch_bounds__(MF_THREADS)
 mf_scores_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi,
@@ -948,8 +952,6 @@ struct MfLayout {
     size_t bytes;
 };
 
-constexpr int MF_MAX_GRID = 148 * 16;
-
 MfLayout mf_layout(void* base, int64_t B, int64_t U, int64_t I) {
     WsCarver ws(base);
     MfLayout l;
@@ -1019,6 +1021,8 @@ void launch_long(int lpr, cudaStream_t st, const MfDev& a) {
     }
 }
 
+bool v2_eligible(const slb_mf_step_args* x);
+
 int validate(const slb_mf_step_args* x) {
     SLB_REQUIRE(x != nullptr, "mf_train_step: null args");
     SLB_REQUIRE(x->batch > 0, "mf_train_step: batch must be > 0");
@@ -1041,7 +1045,8 @@ int validate(const slb_mf_step_args* x) {
         }
     } else {
         SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT, "mf_train_step: bad grad_mode");
-        SLB_REQUIRE(x->urows && x->gWu && x->gbu && x->irows && x->gWi && x->gbi && x->compact_counts,
+        // the planned step updates both tables in place and never materialises the compact rows
+        SLB_REQUIRE(v2_eligible(x) || (x->urows && x->gWu && x->gbu && x->irows && x->gWi && x->gbi && x->compact_counts),
                     "mf_train_step: compact mode needs urows/gWu/gbu/irows/gWi/gbi/compact_counts");
     }
     SLB_REQUIRE(x->opt >= SLB_OPT_NONE && x->opt <= SLB_OPT_ADAGRAD, "mf_train_step: bad optimizer");
@@ -1170,6 +1175,180 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     return SLB_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Planned two-kernel step (mf_v2.cuh): workspace layout and launches.
+// ---------------------------------------------------------------------------
+struct V2Layout {
+    PlanDev plan[2];
+    StepV2 st;
+    size_t bytes;
+};
+
+V2Layout v2_layout(void* base, int64_t B, int64_t U, int64_t I, int D) {
+    WsCarver ws(base);
+    V2Layout l;
+    l.st.done = ws.take<int32_t>(8);                 // zero at rest
+    for (int k = 0; k < 2; ++k) {
+        PlanDev& p = l.plan[k];
+        SegIndex& s = p.seg;
+        s.R = U + I;
+        s.Rpad = (s.R + SEG_SCAN_TILE - 1) / SEG_SCAN_TILE * SEG_SCAN_TILE;
+        s.ntiles = s.Rpad / SEG_SCAN_TILE;
+        s.Tmax = 3 * B;
+        s.cnt = ws.take<int32_t>(s.Rpad);            // zero at rest
+        s.off = ws.take<int32_t>(s.Rpad);
+        s.sid = ws.take<int32_t>(s.Rpad);
+        s.status = ws.take<unsigned long long>(s.ntiles);
+        s.ticket = ws.take<int32_t>(8);
+        s.totals = s.ticket + 4;
+        s.seg_row = ws.take<int32_t>(3 * B + 1);
+        s.seg_start = ws.take<int32_t>(3 * B + 2);
+        s.long_list = ws.take<int32_t>(3 * B / 16 + 2);
+        s.members = nullptr; s.long_tmp = nullptr; s.long_bits = nullptr; s.long_words = 0;
+        s.long_cap = 0;
+        p.mu = ws.take<URec>(B + 1);
+        p.mi = ws.take<IRec>(2 * B + 1);
+        p.mu_tmp = ws.take<URec>(B + 1);
+        p.mi_tmp = ws.take<IRec>(2 * B + 1);
+        p.words = (2 * B + 31) / 32;
+        p.bits = ws.take<uint32_t>(static_cast<size_t>(SEG_LONG_CTAS) * 2 * p.words);
+        p.B = B; p.U = U; p.I = I;
+        p.err = nullptr; p.users = nullptr; p.items = nullptr; p.negs = nullptr;
+    }
+    l.st.t_g = ws.take<float>(2 * B);
+    l.st.stash = ws.take<float>(static_cast<size_t>(B) * D);
+    l.st.partial = ws.take<float>(MF_MAX_GRID);
+    l.st.partial_long = ws.take<float>(SEG_LONG_CTAS * 4);
+    l.bytes = ws.bytes();
+    return l;
+}
+
+bool v2_dim_ok(int D) { return D == 8 || D == 16 || D == 32 || D == 64 || D == 128; }
+
+bool v2_eligible(const slb_mf_step_args* x) {
+    if (x->fused_workspace == nullptr || x->loss == SLB_LOSS_ADAPTIVE_HINGE || x->opt == SLB_OPT_NONE ||
+        !v2_dim_ok(x->dim) || x->pos_out != nullptr || x->neg_out != nullptr)
+        return false;
+    // single GPU: both tables updated in place (compact mode, nothing materialised); sharded item
+    // rows: users updated in place, the dense item gradient handed out (dWi / dbi)
+    if (x->opt_users_only) return x->grad_mode == SLB_GRAD_DENSE && x->dWi != nullptr && x->dbi != nullptr;
+    return x->grad_mode == SLB_GRAD_COMPACT;
+}
+
+int v2_launch_plan(const slb_mf_step_args* x, PlanDev p, int32_t* err, const int64_t* users, const int64_t* items,
+                   const int64_t* negs, int64_t B, cudaStream_t st) {
+    p.B = B; p.users = users; p.items = items; p.negs = negs; p.err = err;
+    p.seg.long_cap = seg_sort_cap(lpr_for_dim(x->dim));
+    const int sms = slb_sms();
+    int g = static_cast<int>((B + 255) / 256);
+    if (g > sms * 8) g = sms * 8;
+    plan_count_kernel<<<g, 256, 0, st>>>(p);
+    SLB_LAUNCH_CHECK("plan_count_kernel");
+    seg_scan_launch(p.seg, p.U, st);
+    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    plan_fill_kernel<<<g, 256, 0, st>>>(p);
+    SLB_LAUNCH_CHECK("plan_fill_kernel");
+    int64_t tiles = ((3 * B + 31) / 32 + 3) / 4;
+    int sg = static_cast<int>(tiles < static_cast<int64_t>(sms) * 16 ? tiles : static_cast<int64_t>(sms) * 16);
+    plan_sort_kernel<<<sg, 128, 0, st>>>(p, p.seg.long_cap);
+    SLB_LAUNCH_CHECK("plan_sort_kernel");
+    plan_sort_long_kernel<<<SEG_LONG_CTAS, 256, 0, st>>>(p);          // no-op unless hot rows exist
+    SLB_LAUNCH_CHECK("plan_sort_long_kernel");
+    return SLB_OK;
+}
+
+MfDev v2_dev(const slb_mf_step_args* x, int64_t B, float* loss_out) {
+    MfDev a = {};
+    a.B = B; a.NB = x->norm_batch > 0 ? x->norm_batch : B; a.T = 2 * B;
+    a.loss = x->loss; a.n_neg = 1;
+    a.U = x->num_users; a.I = x->num_items; a.D = x->dim;
+    a.Wu = x->Wu; a.Wi = x->Wi; a.bu = x->bu; a.bi = x->bi;
+    a.loss_out = loss_out;
+    a.opt = x->opt; a.lr = x->lr; a.wd = x->weight_decay; a.eps = x->eps;
+    a.sWu = x->state_Wu; a.sWi = x->state_Wi; a.sbu = x->state_bu; a.sbi = x->state_bi;
+    a.frozen_a = -1; a.frozen_b = -1;
+    if (x->opt_users_only) { a.dWi = x->dWi; a.dbi = x->dbi; }      // item kernel hands the gradient out
+    return a;
+}
+
+template <int LPR, int LOSS>
+void v2_user_launch(const MfDev& a, const PlanDev& p, const StepV2& v, bool small, int grid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(256 / LPR) * (LPR * 4 + 4) * sizeof(float);
+    mf_user_long_kernel<LPR, LOSS><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a, p, v);
+    if (small) mf_user_kernel<LPR, LOSS, 8><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
+    else mf_user_kernel<LPR, LOSS, 32><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
+}
+
+template <int LPR>
+void v2_user_dispatch(const MfDev& a, const PlanDev& p, const StepV2& v, bool small, int grid, cudaStream_t st) {
+    switch (a.loss) {
+        case SLB_LOSS_POINTWISE: v2_user_launch<LPR, SLB_LOSS_POINTWISE>(a, p, v, small, grid, st); break;
+        case SLB_LOSS_BPR: v2_user_launch<LPR, SLB_LOSS_BPR>(a, p, v, small, grid, st); break;
+        default: v2_user_launch<LPR, SLB_LOSS_HINGE>(a, p, v, small, grid, st); break;
+    }
+}
+
+template <int LPR>
+void v2_item_launch(const MfDev& a, const PlanDev& p, const StepV2& v, bool small, int grid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(256 / LPR) * (LPR * 4 + 4) * sizeof(float);
+    mf_item_long_kernel<LPR><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a, p, v);
+    if (small) mf_item_kernel<LPR, 8><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v);
+    else mf_item_kernel<LPR, 32><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v);
+}
+
+// phases: 1 plan, 2 user kernels (forward + user update), 4 item kernels
+int v2_launch_step(const slb_mf_step_args* x, const V2Layout& l, int slot, int32_t* err, const int64_t* users,
+                   const int64_t* items, const int64_t* negs, int64_t B, float* loss_out, cudaStream_t st,
+                   int phases) {
+    if (phases & 1) {
+        const int rc = v2_launch_plan(x, l.plan[slot], err, users, items, negs, B, st);
+        if (rc != SLB_OK) return rc;
+    }
+    PlanDev p = l.plan[slot];
+    p.B = B; p.users = users; p.items = items; p.negs = negs; p.err = err;
+    p.seg.long_cap = seg_sort_cap(lpr_for_dim(x->dim));
+    const MfDev a = v2_dev(x, B, loss_out);
+    const int sms = slb_sms();
+    const int lpr = x->dim / 4;
+    if (phases & 2) {
+        const bool small = B < static_cast<int64_t>(sms) * 24 * 32;
+        const int64_t tw = ((B + (small ? 8 : 32) - 1) / (small ? 8 : 32) + 3) / 4;
+        const int grid = static_cast<int>(tw < MF_MAX_GRID ? (tw < 1 ? 1 : tw) : MF_MAX_GRID);
+        switch (lpr) {
+            case 2: v2_user_dispatch<2>(a, p, l.st, small, grid, st); break;
+            case 4: v2_user_dispatch<4>(a, p, l.st, small, grid, st); break;
+            case 8: v2_user_dispatch<8>(a, p, l.st, small, grid, st); break;
+            case 16: v2_user_dispatch<16>(a, p, l.st, small, grid, st); break;
+            default: v2_user_dispatch<32>(a, p, l.st, small, grid, st); break;
+        }
+        SLB_LAUNCH_CHECK("mf_user_kernel");
+    }
+    if (phases & 4) {
+        const bool small = 2 * B < static_cast<int64_t>(sms) * 24 * 32;
+        const int64_t tw = ((2 * B + (small ? 8 : 32) - 1) / (small ? 8 : 32) + 3) / 4;
+        const int grid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? (tw < 1 ? 1 : tw) : static_cast<int64_t>(sms) * 16);
+        switch (lpr) {
+            case 2: v2_item_launch<2>(a, p, l.st, small, grid, st); break;
+            case 4: v2_item_launch<4>(a, p, l.st, small, grid, st); break;
+            case 8: v2_item_launch<8>(a, p, l.st, small, grid, st); break;
+            case 16: v2_item_launch<16>(a, p, l.st, small, grid, st); break;
+            default: v2_item_launch<32>(a, p, l.st, small, grid, st); break;
+        }
+        SLB_LAUNCH_CHECK("mf_item_kernel");
+    }
+    return SLB_OK;
+}
+
+int v2_check_ws(const slb_mf_step_args* x) {
+    const size_t need = v2_layout(nullptr, x->batch, x->num_users, x->num_items, x->dim).bytes;
+    if (x->fused_workspace_bytes < need) {
+        slb_set_error("mf_train_step: fused workspace too small (%zu < %zu)", x->fused_workspace_bytes, need);
+        return SLB_ENOSPC;
+    }
+    return SLB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1185,9 +1364,22 @@ int64_t slb_mf_compact_rows(int64_t batch, int32_t n_neg, int32_t loss, int32_t 
     return 2 * batch;  // positive + selected negative term per interaction
 }
 
+size_t slb_mf_fused_workspace_bytes(int64_t batch, int64_t num_users, int64_t num_items, int32_t dim) {
+    if (batch <= 0 || !v2_dim_ok(dim)) return 0;
+    return v2_layout(nullptr, batch, num_users, num_items, dim).bytes;
+}
+
 int slb_mf_train_step(const slb_mf_step_args* x, slb_stream_t stream) {
     const int rc = validate(x);
     if (rc != SLB_OK) return rc;
+    if (v2_eligible(x)) {
+        const int r2 = v2_check_ws(x);
+        if (r2 != SLB_OK) return r2;
+        const V2Layout l = v2_layout(x->fused_workspace, x->batch, x->num_users, x->num_items, x->dim);
+        MfLayout old = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
+        return v2_launch_step(x, l, 0, old.err, x->users, x->items, x->negs, x->batch, x->loss_out,
+                              static_cast<cudaStream_t>(stream), 7);
+    }
     return launch_step(x, x->users, x->items, x->negs, x->batch, x->loss_out,
                        static_cast<cudaStream_t>(stream));
 }
@@ -1195,12 +1387,21 @@ int slb_mf_train_step(const slb_mf_step_args* x, slb_stream_t stream) {
 int slb_mf_train_step_phases(const slb_mf_step_args* x, int32_t phases, slb_stream_t stream) {
     const int rc = validate(x);
     if (rc != SLB_OK) return rc;
+    if (v2_eligible(x)) {          // planned step: 1 plan, 2 user kernels, 4 item kernels
+        const int r2 = v2_check_ws(x);
+        if (r2 != SLB_OK) return r2;
+        const V2Layout l = v2_layout(x->fused_workspace, x->batch, x->num_users, x->num_items, x->dim);
+        MfLayout old = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
+        return v2_launch_step(x, l, (phases >> 8) & 1, old.err, x->users, x->items, x->negs, x->batch, x->loss_out,
+                              static_cast<cudaStream_t>(stream), phases & 7);
+    }
     return launch_step(x, x->users, x->items, x->negs, x->batch, x->loss_out,
                        static_cast<cudaStream_t>(stream), phases);
 }
 
-int slb_mf_fit_epoch(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
-                     const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream) {
+static int fit_epoch_impl(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
+                          const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream,
+                          const int64_t* wait_steps, void* const* wait_events, int32_t n_waits) {
     slb_mf_step_args tmp = *x;
     tmp.users = users; tmp.items = items; tmp.negs = negs; tmp.loss_out = losses_out;
     const int rc = validate(&tmp);
@@ -1208,17 +1409,98 @@ int slb_mf_fit_epoch(const slb_mf_step_args* x, const int64_t* users, const int6
     SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT && x->opt != SLB_OPT_NONE,
                 "mf_fit_epoch: needs compact grads and a fused optimizer");
     SLB_REQUIRE(n > 0, "mf_fit_epoch: n must be > 0");
+    cudaStream_t main_st = static_cast<cudaStream_t>(stream);
+    if (v2_eligible(&tmp)) {
+        // planned step: the plan of step k+1 (integer work on ids only) is enqueued on the plan
+        // stream before the float kernels of step k, double-buffered, so it runs under them
+        const int r2 = v2_check_ws(&tmp);
+        if (r2 != SLB_OK) return r2;
+        const V2Layout l = v2_layout(x->fused_workspace, x->batch, x->num_users, x->num_items, x->dim);
+        MfLayout old = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
+        cudaStream_t plan_st = x->plan_stream ? static_cast<cudaStream_t>(x->plan_stream) : main_st;
+        const bool two = plan_st != main_st;
+        const int64_t nsteps = (n + x->batch - 1) / x->batch;
+        cudaEvent_t ev_plan[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_in = nullptr;
+        int rc2 = SLB_OK;
+        if (two) {
+            bool ok = cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) == cudaSuccess;
+            for (int k = 0; k < 2 && ok; ++k)
+                ok = cudaEventCreateWithFlags(&ev_plan[k], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { slb_set_error("mf_fit_epoch: cannot create events"); rc2 = SLB_ECUDA; }
+            if (rc2 == SLB_OK) {           // the plan stream starts after everything queued on the main stream so far
+                cudaEventRecord(ev_in, main_st);
+                cudaStreamWaitEvent(plan_st, ev_in, 0);
+            }
+        }
+        int next_wait = 0;
+        auto plan_of = [&](int64_t k) {
+            const int64_t lo = k * x->batch;
+            const int64_t B = n - lo < x->batch ? n - lo : x->batch;
+            const int slot = static_cast<int>(k & 1);
+            // inputs of step k onwards become ready with this event (e.g. a chunk of negatives drawn
+            // on another stream); the float kernels inherit the dependency through ev_plan
+            while (next_wait < n_waits && wait_steps[next_wait] <= k) {
+                cudaStreamWaitEvent(plan_st, static_cast<cudaEvent_t>(wait_events[next_wait]), 0);
+                ++next_wait;
+            }
+            if (two && k >= 2) cudaStreamWaitEvent(plan_st, ev_done[slot], 0);      // slot free again
+            const int r = v2_launch_plan(&tmp, l.plan[slot], old.err, users + lo, items + lo, negs + lo, B, plan_st);
+            if (two) cudaEventRecord(ev_plan[slot], plan_st);
+            return r;
+        };
+        if (rc2 == SLB_OK) rc2 = plan_of(0);
+        for (int64_t k = 0; k < nsteps && rc2 == SLB_OK; ++k) {
+            const int64_t lo = k * x->batch;
+            const int64_t B = n - lo < x->batch ? n - lo : x->batch;
+            const int slot = static_cast<int>(k & 1);
+            if (k + 1 < nsteps) rc2 = plan_of(k + 1);
+            if (rc2 != SLB_OK) break;
+            if (two) cudaStreamWaitEvent(main_st, ev_plan[slot], 0);
+            rc2 = v2_launch_step(&tmp, l, slot, old.err, users + lo, items + lo, negs + lo, B, losses_out + k,
+                                 main_st, 6);
+            if (two) cudaEventRecord(ev_done[slot], main_st);
+        }
+        if (two) {
+            // later work on the plan stream must not overtake this epoch's float kernels
+            if (ev_in) { cudaEventRecord(ev_in, main_st); cudaStreamWaitEvent(plan_st, ev_in, 0); }
+            for (int k = 0; k < 2; ++k) {
+                if (ev_plan[k]) cudaEventDestroy(ev_plan[k]);
+                if (ev_done[k]) cudaEventDestroy(ev_done[k]);
+            }
+            if (ev_in) cudaEventDestroy(ev_in);
+        }
+        return rc2;
+    }
     int64_t step = 0;
+    int next_wait = 0;
     for (int64_t lo = 0; lo < n; lo += x->batch, ++step) {
         const int64_t B = n - lo < x->batch ? n - lo : x->batch;
+        while (next_wait < n_waits && wait_steps[next_wait] <= step) {
+            cudaStreamWaitEvent(main_st, static_cast<cudaEvent_t>(wait_events[next_wait]), 0);
+            ++next_wait;
+        }
         // adaptive hinge: negatives of step k are the flat [B*n_neg] block the
         // reference's per-batch randint would have produced (implicit.py:256-259)
         const int64_t* ng = negs + lo * x->n_neg;
-        const int r = launch_step(x, users + lo, items + lo, ng, B, losses_out + step,
-                                  static_cast<cudaStream_t>(stream));
+        const int r = launch_step(x, users + lo, items + lo, ng, B, losses_out + step, main_st);
         if (r != SLB_OK) return r;
     }
     return SLB_OK;
+}
+
+int slb_mf_fit_epoch(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
+                     const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream) {
+    return fit_epoch_impl(x, users, items, negs, n, losses_out, stream, nullptr, nullptr, 0);
+}
+
+int slb_mf_fit_epoch_events(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
+                            const int64_t* negs, int64_t n, float* losses_out, slb_stream_t stream,
+                            const int64_t* wait_steps, void* const* wait_events, int32_t n_waits) {
+    SLB_REQUIRE(n_waits == 0 || (wait_steps && wait_events), "mf_fit_epoch_events: null wait list");
+    for (int32_t k = 1; k < n_waits; ++k)
+        SLB_REQUIRE(wait_steps[k] >= wait_steps[k - 1], "mf_fit_epoch_events: wait_steps must ascend");
+    return fit_epoch_impl(x, users, items, negs, n, losses_out, stream, wait_steps, wait_events, n_waits);
 }
 
 int slb_mf_scores(const float* Wu, const float* Wi, const float* bu, const float* bi,

@@ -27,6 +27,7 @@ constexpr int SEG_LONG_CTAS = 8;
 struct SegIndex {
     int32_t* cnt;        // [Rpad] zero at rest
     int32_t* off;        // [Rpad] exclusive prefix of cnt (valid where cnt > 0)
+    int32_t* sid;        // [Rpad] or NULL: segment id of a touched row (planned step, mf_v2.cuh)
     unsigned long long* status;  // [ntiles] look-back words, zero at rest
     int32_t* ticket;     // [1] dynamic tile id, zero at rest
     int32_t* totals;     // [4] nseg, nterms, nsegA, (unused)
@@ -54,6 +55,7 @@ static inline SegIndex seg_index_carve(WsCarver& ws, int64_t R, int64_t Tmax) {
     s.Tmax = Tmax;
     s.cnt = ws.take<int32_t>(s.Rpad);
     s.off = ws.take<int32_t>(s.Rpad);
+    s.sid = nullptr;
     s.status = ws.take<unsigned long long>(s.ntiles);
     s.ticket = ws.take<int32_t>(8);
     s.totals = s.ticket + 4;
@@ -165,6 +167,7 @@ seg_scan_kernel(SegIndex s, int64_t RA) {
         if (row == RA) s.totals[2] = static_cast<int32_t>(seg);
         if (c[i] != 0) {
             s.off[row] = static_cast<int32_t>(run);
+            if (s.sid) s.sid[row] = static_cast<int32_t>(seg);
             s.seg_row[seg] = static_cast<int32_t>(row);
             s.seg_start[seg] = static_cast<int32_t>(run);
             if (s.long_cap > 0 && c[i] > s.long_cap) s.long_list[atomicAdd(s.totals + 3, 1)] = static_cast<int32_t>(seg);

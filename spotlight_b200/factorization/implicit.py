@@ -22,6 +22,7 @@ There is no CPU route: ``use_cuda=False`` raises at ``fit``.
 """
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -48,6 +49,17 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
+_PLAN_STREAMS = {}
+
+
+def _plan_stream(device):
+    """Per-device stream for the planned step's integer plan kernels (csrc/mf_v2.cuh)."""
+    key = torch.device(device).index
+    if key not in _PLAN_STREAMS:
+        _PLAN_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _PLAN_STREAMS[key]
+
+
 def _to_device_ids(ids, device):
     """Host id array -> int64 CUDA tensor (narrow on the wire, widened on the device)."""
     return _to_device_narrow(ids, device).long()
@@ -62,6 +74,11 @@ def _to_device_narrow(ids, device):
     host = torch.from_numpy(arr)
     return host.to(device, non_blocking=host.is_pinned())     # page-locked callers get an async DMA
 
+
+# route pointwise / bpr / hinge epochs through the planned two-kernel step (csrc/mf_v2.cuh);
+# False selects the first-generation step (kept for A/B measurements and as the reference
+# implementation of the compact-gradient mode)
+PLANNED_STEP = True
 
 # epochs at least this long take their permutation from the device shuffle (csrc/shuffle.cu);
 # both paths are bit-exact with numpy, so the threshold is a speed knob only
@@ -266,7 +283,7 @@ class ImplicitFactorizationModel(object):
             if np.isnan(epoch_loss) or epoch_loss == 0.0:
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
 
-    def _run_epoch_device(self, users, items, chunk_batches=64, after_sampling=None):
+    def _run_epoch_device(self, users, items, chunk_batches=48, after_sampling=None):
         """The epoch pipeline over device-resident (already shuffled) ids.
 
         Negatives are drawn chunk by chunk on a side stream (the MT19937 block
@@ -293,50 +310,36 @@ class ImplicitFactorizationModel(object):
             # the generator lives on the device for the whole epoch: the draws chain without
             # a host round trip and finish() hands the state back once (spotlight_b200/rng.py)
             stream = _rng.DeviceStream(self._random_state, dev)
-        drawn = [0]
-        total = n * n_neg
-
-        def draw(count):
-            lo_v = drawn[0]
-            drawn[0] += count * n_neg
-            with torch.cuda.stream(side):
-                negs = stream.draw(self._num_items, count * n_neg, out=negs_all[lo_v:drawn[0]])
+        # All of the epoch's draws are enqueued first (side stream), in chunks of up to
+        # `chunk_batches` minibatches, each followed by an event; then ONE C call enqueues every
+        # training step, making its streams wait for the event of the chunk a step belongs to.
+        # Nothing on the host waits in between.  A chunk costs one jump round + one block-fill
+        # round whatever its size (up to the one-round reach of the jump table, ~31 M values), so
+        # the first chunk is as large as the others: only ~0.1 ms more exposed than a one-batch
+        # chunk, and the latency-bound generator never competes with the training kernels for a
+        # short epoch.
+        waits = []
+        lo = 0
+        with torch.cuda.stream(side):
+            while lo < n:
+                cur = min(chunk, n - lo)
+                stream.draw(self._num_items, cur * n_neg, out=negs_all[lo * n_neg:(lo + cur) * n_neg])
                 ev = torch.cuda.Event()
                 ev.record(side)
-                if after_sampling is not None and drawn[0] == total:
-                    # waits for the sampler only; the main stream still holds the previous
-                    # chunk's training steps
-                    stream.finish()
-            if after_sampling is not None and drawn[0] == total:
-                after_sampling()                # RandomState is final for this epoch
-            return negs, ev
-
-        keep, parts = [], []
-        lo = 0
-        # chunks grow 1, 2, 4, ... batches up to `chunk_batches`: only the first
-        # (one-batch) draw is exposed, every later one hides behind training steps
-        cur = min(B, n)
-        nxt = draw(cur)
-        while lo < n:
-            cnt = cur
-            negs, ev = nxt
-            main.wait_event(ev)
-            parts.append(self._fit_epoch_pipeline(users[lo:lo + cnt], items[lo:lo + cnt], negs,
-                                                  sync=False))
-            keep.append(negs)
-            lo += cnt
-            if lo < n:
-                cur = min(min(2 * cnt, chunk), n - lo)
-                nxt = draw(cur)
+                waits.append((lo // B, ev))
+                lo += cur
+        losses = self._fit_epoch_pipeline(users, items, negs_all, sync=False, waits=waits)
         with torch.cuda.stream(side):
-            stream.finish()                     # no-op when the hook above already ran it
-        host = torch.cat(parts).cpu().numpy().astype(np.float64)       # one sync per epoch
+            stream.finish()                     # waits for the sampler only: RandomState is final
+        if after_sampling is not None:
+            after_sampling()                    # next epoch's shuffle, under this epoch's training
+        host = losses.cpu().numpy().astype(np.float64)                  # one sync per epoch
         ws = ops.workspace('mf%d_%d' % (self._num_users, self._num_items), 0, dev)
         if ops.workspace_error_flag(ws):
             raise ValueError('ids out of range reached the device kernels')
         return float(host.sum() / len(host))
 
-    def _fit_epoch_pipeline(self, users, items, negatives, sync=True):
+    def _fit_epoch_pipeline(self, users, items, negatives, sync=True, waits=()):
         """One C call enqueues every minibatch step of ``users``/``items``; returns the
         device tensor of per-batch losses (``sync=False``) or their mean."""
         net, opt = self._net, self._optimizer
@@ -348,19 +351,33 @@ class ImplicitFactorizationModel(object):
         with torch.no_grad():
             a = ops.mf_step_args(Wu, Wi, bu, bi, users, items, negatives, self._loss, n_neg,
                                  batch=min(B, n))
-            rows = lib.slb_mf_compact_rows(a.batch, n_neg, a.loss, 0)
-            D = a.dim
-            urows = torch.empty(rows, dtype=torch.int64, device=dev)
-            irows = torch.empty(rows, dtype=torch.int64, device=dev)
-            gWu = torch.empty((rows, D), dtype=torch.float32, device=dev)
-            gWi = torch.empty((rows, D), dtype=torch.float32, device=dev)
-            gbu = torch.empty(rows, dtype=torch.float32, device=dev)
-            gbi = torch.empty(rows, dtype=torch.float32, device=dev)
-            counts = torch.zeros(2, dtype=torch.int32, device=dev)
             a.grad_mode = _lib.GRAD_COMPACT
-            a.urows, a.gWu, a.gbu = urows.data_ptr(), gWu.data_ptr(), gbu.data_ptr()
-            a.irows, a.gWi, a.gbi = irows.data_ptr(), gWi.data_ptr(), gbi.data_ptr()
-            a.compact_counts = counts.data_ptr()
+            # planned two-kernel step (plan + user kernel + item kernel, csrc/mf_v2.cuh) whenever the
+            # library supports the shape; otherwise the first-generation step with compact gradients
+            fused_need = 0
+            if self._loss != 'adaptive_hinge' and PLANNED_STEP:
+                fused_need = lib.slb_mf_fused_workspace_bytes(a.batch, a.num_users, a.num_items, a.dim)
+            if fused_need:
+                fws = ops.workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, a.batch),
+                                    fused_need, dev)
+                a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
+                if not os.environ.get('SLB_PLAN_SAME_STREAM'):      # A/B switch for measurements
+                    a.plan_stream = _plan_stream(dev).cuda_stream
+                keep = (fws,)
+            else:
+                rows = lib.slb_mf_compact_rows(a.batch, n_neg, a.loss, 0)
+                D = a.dim
+                urows = torch.empty(rows, dtype=torch.int64, device=dev)
+                irows = torch.empty(rows, dtype=torch.int64, device=dev)
+                gWu = torch.empty((rows, D), dtype=torch.float32, device=dev)
+                gWi = torch.empty((rows, D), dtype=torch.float32, device=dev)
+                gbu = torch.empty(rows, dtype=torch.float32, device=dev)
+                gbi = torch.empty(rows, dtype=torch.float32, device=dev)
+                counts = torch.zeros(2, dtype=torch.int32, device=dev)
+                a.urows, a.gWu, a.gbu = urows.data_ptr(), gWu.data_ptr(), gbu.data_ptr()
+                a.irows, a.gWi, a.gbi = irows.data_ptr(), gWi.data_ptr(), gbi.data_ptr()
+                a.compact_counts = counts.data_ptr()
+                keep = (urows, irows, gWu, gWi, gbu, gbi, counts)
             hp = opt.fused_hparams()
             a.opt, a.lr, a.weight_decay, a.eps = opt.fused_kind, hp['lr'], hp['weight_decay'], hp['eps']
             if opt.fused_kind == _lib.OPT_ADAGRAD:
@@ -371,8 +388,12 @@ class ImplicitFactorizationModel(object):
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             n_steps = (n + B - 1) // B
             losses = torch.empty(n_steps, dtype=torch.float32, device=dev)
-            rc = lib.slb_mf_fit_epoch(ctypes.byref(a), ops._ptr(users), ops._ptr(items),
-                                      ops._ptr(negatives), n, ops._ptr(losses), ops._stream())
+            # steps wait (on the device) for the event of the chunk of negatives they read
+            w_steps = (ctypes.c_int64 * max(1, len(waits)))(*[int(k) for k, _ in waits])
+            w_events = (ctypes.c_void_p * max(1, len(waits)))(*[ev.cuda_event for _, ev in waits])
+            rc = lib.slb_mf_fit_epoch_events(ctypes.byref(a), ops._ptr(users), ops._ptr(items),
+                                             ops._ptr(negatives), n, ops._ptr(losses), ops._stream(),
+                                             w_steps, w_events, len(waits))
             _lib.check(rc, 'mf_fit_epoch')
             if not sync:
                 return losses

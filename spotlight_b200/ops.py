@@ -299,6 +299,47 @@ def _(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, want_scores):
             torch.empty_like(Wu), torch.empty_like(Wi), torch.empty_like(bu), torch.empty_like(bi))
 
 
+def mf_train_step_inplace(Wu, Wi, bu, bi, users, items, negs, loss, opt_kind, lr, states=None,
+                          weight_decay=0.0, eps=1e-10, planned=True):
+    """One minibatch with the row-wise optimizer fused in: parameters (and Adagrad ``states`` =
+    (sWu, sWi, sbu, sbi)) are updated in place, the minibatch loss is returned.
+
+    ``planned`` selects the two-kernel planned step (csrc/mf_v2.cuh) when the library supports
+    the shape; otherwise the first-generation step with compact gradients runs.  This is the
+    body of one iteration of ``slb_mf_fit_epoch`` (spotlight/factorization/implicit.py:229-243).
+    """
+    require_cuda(Wu, Wi, bu, bi, users, items, negs)
+    lib = _lib.load()
+    users, items, negs = _i64c(users).reshape(-1), _i64c(items).reshape(-1), _i64c(negs).reshape(-1)
+    B = users.numel()
+    dev = Wu.device
+    with torch.no_grad():
+        a = mf_step_args(Wu, Wi, bu, bi, users, items, negs, loss, 1)
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+        a.loss_out = loss_out.data_ptr()
+        a.grad_mode = _lib.GRAD_COMPACT
+        a.opt, a.lr, a.weight_decay, a.eps = int(opt_kind), float(lr), float(weight_decay), float(eps)
+        if opt_kind == _lib.OPT_ADAGRAD:
+            a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [t.data_ptr() for t in states]
+        keep = []
+        need2 = lib.slb_mf_fused_workspace_bytes(B, a.num_users, a.num_items, a.dim) if planned else 0
+        if need2 and a.loss != 3:
+            fws = workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, B), need2, dev)
+            a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
+        else:
+            rows = lib.slb_mf_compact_rows(B, 1, a.loss, 0)
+            keep = [torch.empty(rows, dtype=torch.int64, device=dev), torch.empty(rows, dtype=torch.int64, device=dev),
+                    torch.empty((rows, a.dim), device=dev), torch.empty((rows, a.dim), device=dev),
+                    torch.empty(rows, device=dev), torch.empty(rows, device=dev),
+                    torch.zeros(2, dtype=torch.int32, device=dev)]
+            a.urows, a.irows, a.gWu, a.gWi, a.gbu, a.gbi, a.compact_counts = [t.data_ptr() for t in keep]
+        need = lib.slb_mf_step_workspace_bytes(B, 1, a.loss, a.num_users, a.num_items)
+        ws = workspace('mf%d_%d' % (a.num_users, a.num_items), need, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.slb_mf_train_step(ctypes.byref(a), _stream()), 'mf_train_step')
+    return loss_out.reshape(())
+
+
 @torch.library.custom_op('spotlight_b200::mf_bloom_train_step', mutates_args=())
 def mf_bloom_train_step(Wu: Tensor, Wi: Tensor, bu: Tensor, bi: Tensor, users: Tensor, items: Tensor,
                         negs: Tensor, loss: int, n_neg: int, user_seeds: List[int],

@@ -108,6 +108,13 @@ class GpuBackend(object):
         need = lib.slb_mf_step_workspace_bytes(a.batch, n_neg, a.loss, a.num_users, a.num_items)
         ws = ops.workspace('mf%d_%d' % (a.num_users, a.num_items), need, self.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        # planned two-kernel step (csrc/mf_v2.cuh): user rows updated in place, the item kernel
+        # hands the dense cache-row gradient out for the owners
+        need2 = lib.slb_mf_fused_workspace_bytes(a.batch, a.num_users, a.num_items, a.dim) if n_neg == 1 else 0
+        if need2:
+            fws = ops.workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, a.batch), need2,
+                                self.device)
+            a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
         _lib.check(lib.slb_mf_train_step(ctypes.byref(a), ops._stream()), 'mf_train_step')
         return loss_out.reshape(()), dWi[:n_cache], dbi[:n_cache]
 
@@ -157,6 +164,30 @@ class GpuBackend(object):
         from spotlight_b200.sampling import sample_items
         return sample_items(num_items, count, random_state=random_state, device=self.device)
 
+    def upload_sharded(self, ids, rank, world, group=None):
+        """Host ids -> the full array on this device with 1/world of the PCIe traffic: every
+        rank holds the same host array (single-process semantics), uploads only its slice and
+        the slices meet over NVLink (all-gather)."""
+        arr = np.ascontiguousarray(ids)
+        if arr.dtype not in (np.int32, np.int64):
+            arr = arr.astype(np.int64)
+        n = arr.shape[0]
+        if world == 1 or n < (1 << 16):
+            return self.to_device(arr)
+        per = -(-n // world)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        host = torch.from_numpy(arr[lo:hi])
+        part = torch.zeros(per, dtype=host.dtype, device=self.device)
+        part[:hi - lo].copy_(host, non_blocking=host.is_pinned())
+        full = torch.empty(per * world, dtype=host.dtype, device=self.device)
+        dist.all_gather_into_tensor(full, part, group=group)
+        return full[:n]
+
+    def epoch_sampler(self, num_items, random_state, total):
+        """Chunked global negative stream on a side stream (device-chained draws, one
+        hand-back): draw(count) -> (tensor, event the consumer stream must wait for)."""
+        return _GpuEpochSampler(self.device, num_items, random_state, total)
+
     def seq_local_step(self, E_cache, bias_cache, n_cache, seqs_idx, negs_idx, loss, cnn, norm_count):
         """Fused sequence step on the row cache (ids already remapped onto it; cache
         row 0 is the padding row).  Returns (loss share, dE_cache, dbias_cache, dconv_w, dconv_b)."""
@@ -164,6 +195,45 @@ class GpuBackend(object):
                                  norm_count=norm_count)
         return (out['loss'], out['dE'][:n_cache], out['dbias'].reshape(-1)[:n_cache],
                 out['dconv_w'], out['dconv_b'])
+
+
+class _GpuEpochSampler(object):
+    def __init__(self, device, num_items, random_state, total):
+        from spotlight_b200 import rng
+        from spotlight_b200.factorization.implicit import _side_stream
+        self.dev, self.num_items = torch.device(device), int(num_items)
+        self.side = _side_stream(self.dev)
+        self.out = torch.empty(total, dtype=torch.int64, device=self.dev)
+        self.side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.side):
+            self.stream = rng.DeviceStream(random_state, self.dev)
+        self.done = 0
+
+    def draw(self, count):
+        lo, self.done = self.done, self.done + count
+        with torch.cuda.stream(self.side):
+            self.stream.draw(self.num_items, count, out=self.out[lo:self.done])
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        return self.out[lo:self.done], ev
+
+    def finish(self):
+        with torch.cuda.stream(self.side):
+            self.stream.finish()
+        self.out.record_stream(torch.cuda.current_stream(self.dev))
+
+
+class _HostEpochSampler(object):
+    """Backend-agnostic fallback: one synchronous draw per request (CPU / gloo tests)."""
+
+    def __init__(self, backend, num_items, random_state):
+        self.be, self.num_items, self.rs = backend, num_items, random_state
+
+    def draw(self, count):
+        return self.be.sample(self.num_items, count, self.rs), None
+
+    def finish(self):
+        pass
 
 
 def adagrad_dense_(W, state, grad, lr, eps):
@@ -544,46 +614,73 @@ class ShardedImplicitFactorizationModel(object):
         self.epoch_losses = []
 
     def fit(self, interactions, verbose=False):
-        plan, be, B = self.plan, self.backend, self._batch_size
+        be = self.backend
         n = len(interactions.user_ids)
-        users_dev = be.to_device(interactions.user_ids)
-        items_dev = be.to_device(interactions.item_ids)
+        if hasattr(be, 'upload_sharded'):
+            users_dev = be.upload_sharded(interactions.user_ids, self.rank, self.world, self.mf.group)
+            items_dev = be.upload_sharded(interactions.item_ids, self.rank, self.world, self.mf.group)
+        else:
+            users_dev = be.to_device(interactions.user_ids)
+            items_dev = be.to_device(interactions.item_ids)
         if users_dev.dtype != items_dev.dtype:
             users_dev, items_dev = users_dev.long(), items_dev.long()
-        if n and int(users_dev.max()) >= self._num_users:
-            raise ValueError('Maximum user id greater than number of users in model.')
-        if n and int(items_dev.max()) >= self._num_items:
-            raise ValueError('Maximum item id greater than number of items in model.')
+        if n:
+            umax, imax = torch.stack([users_dev.max(), items_dev.max()]).tolist()      # one sync
+            if umax >= self._num_users:
+                raise ValueError('Maximum user id greater than number of users in model.')
+            if imax >= self._num_items:
+                raise ValueError('Maximum item id greater than number of items in model.')
         for epoch in range(self._n_iter):
             order = be.shuffled_order(n, self._random_state)
             u, i = be.permute(order, users_dev, items_dev)
             del order
-            nn = self._n_neg
-            negs = be.sample(self._num_items, n * nn, self._random_state)
-            # this rank's members of every minibatch, in minibatch order
-            mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
-            edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
-            bounds = torch.searchsorted(mine, edges).tolist()
-            # a minibatch draws len(batch) * n values at once (implicit.py:256-259, 266-275): the
-            # n-block of the member at epoch position p is negs[n*p : n*p + n]
-            mu, mi, mn = u[mine], i[mine], negs.reshape(n, nn)[mine].reshape(-1)
-            bpos = mine % B
-            del i, negs, mine
-            losses = []
-            for k in range(len(bounds) - 1):
-                sl = slice(bounds[k], bounds[k + 1])
-                if self._loss == 'adaptive_hinge':
-                    losses.append(self.mf.step_adaptive(
-                        mu[sl], mi[sl], mn[bounds[k] * nn:bounds[k + 1] * nn], bpos[sl],
-                        u[k * B:(k + 1) * B], nn))
-                else:
-                    losses.append(self.mf.step(mu[sl], mi[sl], mn[sl], self._loss, min(B, n - k * B),
-                                               self._exchange))
-            del u
-            epoch_loss = float(torch.stack(losses).mean()) if losses else 0.0
+            epoch_loss = self._run_epoch_device(u, i)
+            del u, i
             self.epoch_losses.append(epoch_loss)
             if verbose and self.rank == 0:
                 print('Epoch {}: loss {}'.format(epoch, epoch_loss))
             if np.isnan(epoch_loss) or epoch_loss == 0.0:
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
         return self
+
+    def _run_epoch_device(self, u, i, chunk_batches=16):
+        """One epoch over the (already shuffled) global ids ``u`` / ``i``, held identically on
+        every rank's device: global negative stream (chunked, on a side stream where the
+        backend has one), owner partition, and the sharded steps of this rank's members.
+        Returns the epoch loss (mean of the global minibatch losses, implicit.py:240,245)."""
+        plan, be, B, nn = self.plan, self.backend, self._batch_size, self._n_neg
+        n = u.numel()
+        if n == 0:
+            return 0.0
+        # this rank's members of every minibatch, in minibatch order (no dependence on negatives)
+        mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
+        edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
+        bounds = torch.searchsorted(mine, edges).tolist()                   # the epoch's one sync
+        mu, mi = u[mine], i[mine]
+        bpos = mine % B
+        sampler = (be.epoch_sampler(self._num_items, self._random_state, n * nn)
+                   if hasattr(be, 'epoch_sampler') else _HostEpochSampler(be, self._num_items, self._random_state))
+        nsteps = len(bounds) - 1
+        losses = []
+        k, cur = 0, 1
+        while k < nsteps:
+            # one draw per chunk of global minibatches; a minibatch draws len(batch) * n values at
+            # once (implicit.py:256-259, 266-275): the n-block of the member at epoch position p
+            # is negs[n*p : n*p + n]
+            hi_k = min(k + cur, nsteps)
+            lo_e, hi_e = k * B, min(hi_k * B, n)
+            negs, ev = sampler.draw((hi_e - lo_e) * nn)
+            if ev is not None:
+                torch.cuda.current_stream(u.device).wait_event(ev)
+            negs = negs.reshape(hi_e - lo_e, nn)
+            for kk in range(k, hi_k):
+                sl = slice(bounds[kk], bounds[kk + 1])
+                mn = negs[mine[sl] - lo_e].reshape(-1)
+                if self._loss == 'adaptive_hinge':
+                    losses.append(self.mf.step_adaptive(mu[sl], mi[sl], mn, bpos[sl], u[kk * B:(kk + 1) * B], nn))
+                else:
+                    losses.append(self.mf.step(mu[sl], mi[sl], mn, self._loss, min(B, n - kk * B),
+                                               self._exchange))
+            k, cur = hi_k, min(2 * cur, chunk_batches)
+        sampler.finish()
+        return float(torch.stack(losses).mean()) if losses else 0.0

@@ -290,6 +290,140 @@ def test_fused_step_full_size_properties():
     assert torch.count_nonzero(dbu).item() == 0 or dbu.abs().max().item() < 1e-9
 
 
+# ------------------------------------------------- planned two-kernel step
+
+def _planned_problem(U, I, D, B, seed=0, scale=0.3):
+    rs = np.random.RandomState(seed)
+    Wu = (rs.randn(U, D) * scale).astype(np.float32)
+    Wi = (rs.randn(I, D) * scale).astype(np.float32)
+    bu = (rs.randn(U, 1) * 0.1).astype(np.float32)
+    bi = (rs.randn(I, 1) * 0.1).astype(np.float32)
+    users = rs.randint(0, U, B).astype(np.int64)
+    items = rs.randint(0, I, B).astype(np.int64)
+    negs = rs.randint(0, I, B).astype(np.int64)
+    return (Wu, Wi, bu, bi), (users, items, negs)
+
+
+@pytest.mark.parametrize('loss', ['bpr', 'hinge', 'pointwise'])
+@pytest.mark.parametrize('D,B', [(8, 300), (16, 2048), (32, 5000), (64, 70001), (128, 4096)])
+def test_planned_step_sgd_vs_oracle(loss, D, B):
+    """mf_user_kernel + mf_item_kernel (plan, forward, both gradient halves, in-place SGD) against
+    the float64 oracle: the learning rate is chosen so that the update is as large as the
+    weights, which makes the updated table a 1e-5-grade measurement of the gradient itself."""
+    from spotlight_b200 import _lib, ops
+    U, I = 700, 211
+    params, (users, items, negs) = _planned_problem(U, I, D, B, seed=D + B)
+    ref = omf.mf_step(*params, users, items, negs, loss, 1, np.float64)
+    lr = 0.3 / max(np.abs(ref['dWu']).max(), np.abs(ref['dWi']).max())
+    dev_p = [t(p.copy()) for p in params]
+    got_loss = ops.mf_train_step_inplace(*dev_p, t(users), t(items), t(negs), loss, _lib.OPT_SGD, lr)
+    assert_close(got_loss.item(), float(ref['loss']), 1e-5, what='loss')
+    for p0, pd, g, nm in zip(params, dev_p, (ref['dWu'], ref['dWi'], ref['dbu'], ref['dbi']),
+                             ('Wu', 'Wi', 'bu', 'bi')):
+        want = p0.astype(np.float64) - lr * g.reshape(p0.shape)
+        assert_close(pd.cpu().numpy(), want, 4e-6, what=nm)
+        if nm in ('Wu', 'Wi'):                      # untouched rows are bit-identical
+            untouched = np.abs(g).sum(1) == 0
+            assert (pd.cpu().numpy()[untouched] == p0[untouched]).all()
+
+
+def test_planned_step_adagrad_state_and_reproducible():
+    from spotlight_b200 import _lib, ops
+    U, I, D, B = 5000, 900, 64, 30000
+    params, (users, items, negs) = _planned_problem(U, I, D, B, seed=9)
+    ref = omf.mf_step(*params, users, items, negs, 'bpr', 1, np.float64)
+    outs = []
+    for _ in range(2):
+        dev_p = [t(p.copy()) for p in params]
+        states = [torch.zeros_like(p) for p in dev_p]
+        ops.mf_train_step_inplace(*dev_p, t(users), t(items), t(negs), 'bpr', _lib.OPT_ADAGRAD, 0.05,
+                                  states=states)
+        outs.append((dev_p, states))
+    for a, b in zip(outs[0][0] + outs[0][1], outs[1][0] + outs[1][1]):
+        assert torch.equal(a, b), 'planned step is not bit-reproducible'
+    for s_, g, nm in zip(outs[0][1], (ref['dWu'], ref['dWi'], ref['dbu'], ref['dbi']), ('sWu', 'sWi', 'sbu', 'sbi')):
+        assert_close(s_.cpu().numpy().astype(np.float64), (g * g).reshape(tuple(s_.shape)), 2e-5, atol=1e-30, what=nm)
+    # first Adagrad step: w -= lr * g / (|g| + eps)
+    want = params[1].astype(np.float64) - 0.05 * ref['dWi'] / (np.abs(ref['dWi']) + 1e-10)
+    big = np.abs(ref['dWi']) > 1e-7                 # sign(g) is ill-conditioned at g ~ 0
+    assert np.abs(outs[0][0][1].cpu().numpy() - want)[big].max() < 1e-6
+
+
+@pytest.mark.parametrize('opt', ['sgd', 'adagrad'])
+def test_planned_step_equals_first_generation(opt):
+    """Same minibatches through the planned step and through the first-generation
+    (forward / index / backward / apply) step: three steps, Zipf-skewed items so that hot item
+    rows take the long-list kernels on both paths."""
+    from spotlight_b200 import _lib, ops
+    torch.manual_seed(5)
+    U, I, D, B = 50_000, 20_000, 64, 200_000
+    d = dev()
+    base = [torch.randn(U, D, device=d) / D, torch.randn(I, D, device=d) / D,
+            torch.randn(U, 1, device=d) * 0.01, torch.randn(I, 1, device=d) * 0.01]
+    pz = 1.0 / torch.arange(1, I + 1, device=d, dtype=torch.float64)
+    batches = [(torch.randint(0, U, (B,), device=d), torch.multinomial(pz / pz.sum(), B, replacement=True),
+                torch.randint(0, I, (B,), device=d)) for _ in range(3)]
+    batches[1][0][:5000] = 17                     # a hot *user* row too (5000 interactions in one batch)
+    assert int(torch.bincount(batches[0][1]).max()) > 5000
+    kind = _lib.OPT_SGD if opt == 'sgd' else _lib.OPT_ADAGRAD
+    res = {}
+    for planned in (True, False):
+        prm = [x.clone() for x in base]
+        states = [torch.zeros_like(x) for x in prm]
+        losses = [ops.mf_train_step_inplace(*prm, u, i, j, 'bpr', kind, 0.5 if opt == 'sgd' else 0.05,
+                                            states=states, planned=planned).item() for u, i, j in batches]
+        res[planned] = (prm, losses)
+    assert_close(np.array(res[True][1]), np.array(res[False][1]), 1e-6, what='losses')
+    for a, b, nm in zip(res[True][0], res[False][0], ('Wu', 'Wi', 'bu', 'bi')):
+        # two correct fp32 summation orders; Adagrad's first-touch normalisation amplifies them
+        assert_close_dev(a, b, 1e-5 if opt == 'sgd' else 5e-3, what=nm)
+
+
+def test_planned_epoch_full_size_two_streams():
+    """BASELINE config 2 shape through slb_mf_fit_epoch (plan on its own stream, double
+    buffered): 6 steps of B = 524288 equal the same steps issued one by one on one stream."""
+    import ctypes
+    from spotlight_b200 import _lib, ops
+    torch.manual_seed(6)
+    U, I, D, B, K = 1_000_000, 100_000, 64, 524_288, 6
+    d = dev()
+    base = [torch.randn(U, D, device=d) / D, torch.randn(I, D, device=d) / D,
+            torch.zeros(U, 1, device=d), torch.zeros(I, 1, device=d)]
+    users = torch.randint(0, U, (K * B - 1000,), device=d)          # short last batch
+    items = torch.randint(0, I, (K * B - 1000,), device=d)
+    negs = torch.randint(0, I, (K * B - 1000,), device=d)
+    lib = _lib.load()
+    # one by one
+    p1 = [x.clone() for x in base]
+    s1 = [torch.zeros_like(x) for x in p1]
+    l1 = []
+    for k in range(K):
+        sl = slice(k * B, min((k + 1) * B, users.numel()))
+        l1.append(ops.mf_train_step_inplace(*p1, users[sl], items[sl], negs[sl], 'bpr', _lib.OPT_ADAGRAD,
+                                            0.05, states=s1).item())
+    # one C call, plan stream
+    p2 = [x.clone() for x in base]
+    s2 = [torch.zeros_like(x) for x in p2]
+    a = ops.mf_step_args(*p2, users, items, negs, 'bpr', 1, batch=B)
+    a.grad_mode = _lib.GRAD_COMPACT
+    a.opt, a.lr, a.weight_decay, a.eps = _lib.OPT_ADAGRAD, 0.05, 0.0, 1e-10
+    a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [x.data_ptr() for x in s2]
+    fws = ops.workspace('mfv2_%d_%d_%d_%d' % (U, I, D, B), lib.slb_mf_fused_workspace_bytes(B, U, I, D), d)
+    a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
+    ws = ops.workspace('mf%d_%d' % (U, I), lib.slb_mf_step_workspace_bytes(B, 1, 1, U, I), d)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    plan = torch.cuda.Stream()
+    a.plan_stream = plan.cuda_stream
+    losses = torch.empty(K, device=d)
+    _lib.check(lib.slb_mf_fit_epoch(ctypes.byref(a), ops._ptr(users), ops._ptr(items), ops._ptr(negs),
+                                    users.numel(), ops._ptr(losses), ops._stream()), 'fit_epoch')
+    torch.cuda.synchronize()
+    assert_close(losses.cpu().numpy(), np.array(l1), 1e-7, what='losses')
+    for x, y in zip(p1 + s1, p2 + s2):
+        assert torch.equal(x, y), 'two-stream epoch differs from step-by-step'
+    assert not ops.workspace_error_flag(ws)
+
+
 def test_fused_step_config3_size():
     """BASELINE config 3 shape on one GPU (10M users x 1M items x 128, adaptive hinge with
     n = 5 negatives, B = 65536): loss, scores and all gradients vs an fp32 ATen restatement
