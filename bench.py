@@ -326,7 +326,7 @@ def kernel_breakdown(model, users, items, a, steps):
         st.grad_mode = _lib.GRAD_COMPACT
         bufs = dict(loss=torch.empty(1, device=dev))
         if fused_need:
-            bufs['fws'] = ops.workspace('mfv2_%d_%d_%d_%d' % (a.users, a.items, a.dim, B), fused_need, dev)
+            bufs['fws'] = ops.workspace('mfv2_%d_%d_%d' % (a.users, a.items, a.dim), fused_need, dev)
             st.fused_workspace, st.fused_workspace_bytes = bufs['fws'].data_ptr(), bufs['fws'].numel()
         else:
             rows = lib.slb_mf_compact_rows(B, 1, st.loss, 0)

@@ -33,7 +33,7 @@ EXPORTS = (
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
     'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events',
     'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
-    'slb_unique_workspace_bytes', 'slb_unique_bucket',
+    'slb_unique_workspace_bytes', 'slb_unique_bucket', 'slb_shard_gather_batch', 'slb_adagrad_dense',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
     'slb_seq_step_workspace_bytes', 'slb_seq_train_step', 'slb_seq_representation',
 )
@@ -140,6 +140,8 @@ def _declare(lib):
     lib.slb_unique_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_unique_workspace_bytes.restype = c_sz
     lib.slb_unique_bucket.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.slb_shard_gather_batch.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]
+    lib.slb_adagrad_dense.argtypes = [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp]
     lib.slb_loss_workspace_bytes.argtypes = [c_i64]
     lib.slb_loss_workspace_bytes.restype = c_sz
     lib.slb_pairwise_loss.argtypes = [c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,

@@ -1188,15 +1188,20 @@ struct V2Layout {
 V2Layout v2_layout(void* base, int64_t B, int64_t U, int64_t I, int D) {
     WsCarver ws(base);
     V2Layout l;
-    l.st.done = ws.take<int32_t>(8);                 // zero at rest
+    const int64_t R = U + I;
+    const int64_t Rpad = (R + SEG_SCAN_TILE - 1) / SEG_SCAN_TILE * SEG_SCAN_TILE;
+    // zero-at-rest state first, at offsets that do not depend on the batch size: one workspace then
+    // serves any batch up to its capacity (the sharded step's local batch changes every step)
+    l.st.done = ws.take<int32_t>(8);
+    int32_t* cnt[2] = {ws.take<int32_t>(Rpad), ws.take<int32_t>(Rpad)};
     for (int k = 0; k < 2; ++k) {
         PlanDev& p = l.plan[k];
         SegIndex& s = p.seg;
-        s.R = U + I;
-        s.Rpad = (s.R + SEG_SCAN_TILE - 1) / SEG_SCAN_TILE * SEG_SCAN_TILE;
+        s.R = R;
+        s.Rpad = Rpad;
         s.ntiles = s.Rpad / SEG_SCAN_TILE;
         s.Tmax = 3 * B;
-        s.cnt = ws.take<int32_t>(s.Rpad);            // zero at rest
+        s.cnt = cnt[k];
         s.off = ws.take<int32_t>(s.Rpad);
         s.sid = ws.take<int32_t>(s.Rpad);
         s.status = ws.take<unsigned long long>(s.ntiles);

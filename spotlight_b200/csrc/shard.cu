@@ -53,6 +53,38 @@ uq_inverse_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t rows, SegI
     }
 }
 
+// users_out[k] = users[pos[k]] - user_lo, items_out[k] = items[pos[k]],
+// negs_out[k*n + q] = negs[(pos[k] - neg_base)*n + q]: this rank's members of one global minibatch
+__global__ void __launch_bounds__(256)
+shard_gather_batch_kernel(const int64_t* __restrict__ pos, int64_t m, const int64_t* __restrict__ users,
+                          const int64_t* __restrict__ items, const int64_t* __restrict__ negs, int64_t neg_base,
+                          int n_neg, int64_t user_lo, int64_t* __restrict__ users_out,
+                          int64_t* __restrict__ items_out, int64_t* __restrict__ negs_out) {
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < m; k += nth) {
+        const int64_t p = pos[k];
+        users_out[k] = users[p] - user_lo;
+        items_out[k] = items[p];
+        for (int q = 0; q < n_neg; ++q) negs_out[k * n_neg + q] = negs[(p - neg_base) * n_neg + q];
+    }
+}
+
+// torch.optim.Adagrad (lr_decay 0) on a dense shard; zero gradients leave the element unchanged,
+// so this equals the row-wise update of the touched rows
+__global__ void __launch_bounds__(256)
+adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ S, const float* __restrict__ G, int64_t n,
+                     float lr, float eps) {
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += nth) {
+        const float g = G[k];
+        if (g != 0.f) {
+            const float sv = S[k] + g * g;
+            S[k] = sv;
+            W[k] -= lr * g / (sqrtf(sv) + eps);
+        }
+    }
+}
+
 struct UqLayout { int32_t* flags; SegIndex seg; size_t bytes; };
 
 UqLayout uq_layout(void* base, int64_t n, int64_t rows) {
@@ -94,6 +126,31 @@ int slb_unique_bucket(const int64_t* ids, int64_t n, int64_t rows, int64_t chunk
     SLB_LAUNCH_CHECK("uq_emit_kernel");
     uq_inverse_kernel<<<g, 256, 0, st>>>(ids, n, rows, l.seg, inverse);
     SLB_LAUNCH_CHECK("uq_inverse_kernel");
+    return SLB_OK;
+}
+
+int slb_shard_gather_batch(const int64_t* pos, int64_t m, const int64_t* users, const int64_t* items,
+                           const int64_t* negs, int64_t neg_base, int32_t n_neg, int64_t user_lo,
+                           int64_t* users_out, int64_t* items_out, int64_t* negs_out, slb_stream_t stream) {
+    if (m <= 0) return SLB_OK;
+    SLB_REQUIRE(pos && users && items && negs && users_out && items_out && negs_out && n_neg >= 1,
+                "shard_gather_batch: bad arguments");
+    int g = static_cast<int>((m + 255) / 256);
+    if (g > slb_sms() * 8) g = slb_sms() * 8;
+    shard_gather_batch_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(pos, m, users, items, negs, neg_base,
+                                                                               n_neg, user_lo, users_out, items_out, negs_out);
+    SLB_LAUNCH_CHECK("shard_gather_batch_kernel");
+    return SLB_OK;
+}
+
+int slb_adagrad_dense(float* W, float* state, const float* grad, int64_t n, float lr, float eps,
+                      slb_stream_t stream) {
+    if (n <= 0) return SLB_OK;
+    SLB_REQUIRE(W && state && grad, "adagrad_dense: null pointer");
+    int g = static_cast<int>((n + 255) / 256);
+    if (g > slb_sms() * 16) g = slb_sms() * 16;
+    adagrad_dense_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, state, grad, n, lr, eps);
+    SLB_LAUNCH_CHECK("adagrad_dense_kernel");
     return SLB_OK;
 }
 

@@ -358,7 +358,7 @@ class ImplicitFactorizationModel(object):
             if self._loss != 'adaptive_hinge' and PLANNED_STEP:
                 fused_need = lib.slb_mf_fused_workspace_bytes(a.batch, a.num_users, a.num_items, a.dim)
             if fused_need:
-                fws = ops.workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, a.batch),
+                fws = ops.workspace('mfv2_%d_%d_%d' % (a.num_users, a.num_items, a.dim),
                                     fused_need, dev)
                 a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
                 if not os.environ.get('SLB_PLAN_SAME_STREAM'):      # A/B switch for measurements

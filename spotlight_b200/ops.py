@@ -324,7 +324,7 @@ def mf_train_step_inplace(Wu, Wi, bu, bi, users, items, negs, loss, opt_kind, lr
         keep = []
         need2 = lib.slb_mf_fused_workspace_bytes(B, a.num_users, a.num_items, a.dim) if planned else 0
         if need2 and a.loss != 3:
-            fws = workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, B), need2, dev)
+            fws = workspace('mfv2_%d_%d_%d' % (a.num_users, a.num_items, a.dim), need2, dev)
             a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
         else:
             rows = lib.slb_mf_compact_rows(B, 1, a.loss, 0)

@@ -89,11 +89,13 @@ def _scratch(dev, nwords, ws_bytes):
     cur = _SCRATCH.get(key)
     if cur is None or cur[0].numel() < nwords or cur[1].numel() < ws_bytes:
         grow = 1.5 if cur is not None else 1.0
+        # the small page-locked hand-over buffers are made once per (device, stream): cudaHostAlloc
+        # costs milliseconds and must not recur when the device scratch grows mid-run
+        pins = cur[3:] if cur is not None else (torch.empty(_N, dtype=torch.int32).pin_memory(),
+                                                torch.empty(4, dtype=torch.int64).pin_memory())
         cur = (torch.empty(int(nwords * grow), dtype=torch.int32, device=dev),
                torch.empty(int(ws_bytes * grow) + 4096, dtype=torch.uint8, device=dev),
-               torch.empty(4, dtype=torch.int64, device=dev),
-               torch.empty(_N, dtype=torch.int32).pin_memory(),
-               torch.empty(4, dtype=torch.int64).pin_memory())
+               torch.empty(4, dtype=torch.int64, device=dev)) + tuple(pins)
         _SCRATCH[key] = cur
     return cur
 

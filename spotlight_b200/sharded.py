@@ -112,7 +112,7 @@ class GpuBackend(object):
         # hands the dense cache-row gradient out for the owners
         need2 = lib.slb_mf_fused_workspace_bytes(a.batch, a.num_users, a.num_items, a.dim) if n_neg == 1 else 0
         if need2:
-            fws = ops.workspace('mfv2_%d_%d_%d_%d' % (a.num_users, a.num_items, a.dim, a.batch), need2,
+            fws = ops.workspace('mfv2_%d_%d_%d' % (a.num_users, a.num_items, a.dim), need2,
                                 self.device)
             a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
         _lib.check(lib.slb_mf_train_step(ctypes.byref(a), ops._stream()), 'mf_train_step')
@@ -206,6 +206,7 @@ class _GpuEpochSampler(object):
         self.out = torch.empty(total, dtype=torch.int64, device=self.dev)
         self.side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.side):
+            rng.reserve(self.num_items, total, self.dev)     # scratch sized once, before the first draw
             self.stream = rng.DeviceStream(random_state, self.dev)
         self.done = 0
 
@@ -221,6 +222,24 @@ class _GpuEpochSampler(object):
         with torch.cuda.stream(self.side):
             self.stream.finish()
         self.out.record_stream(torch.cuda.current_stream(self.dev))
+
+
+class _Trace(object):
+    """SLB_TRACE=1: host-clock phase times of fit() with a device sync at each mark (diagnostics)."""
+
+    def __init__(self, rank):
+        import os
+        import time
+        self.on = bool(os.environ.get('SLB_TRACE')) and rank == 0
+        self.time = time
+        self.t = time.perf_counter()
+
+    def __call__(self, what):
+        if self.on:
+            torch.cuda.synchronize()
+            now = self.time.perf_counter()
+            print('[trace] %-8s %.2f ms' % (what, (now - self.t) * 1e3), flush=True)
+            self.t = now
 
 
 class _HostEpochSampler(object):
@@ -252,17 +271,21 @@ class ShardState(object):
         self.ulo, self.uhi, self.ilo, self.ihi = ulo, uhi, ilo, ihi
         self.lr, self.eps = float(lr), float(eps)
         dev = torch.device(device)
+        rows = plan.ichunk              # item shards are padded to the common chunk: the whole-shard
+        #                                 exchange (all-gather / reduce-scatter) runs on them directly;
+        #                                 rows past ihi - ilo stay zero and are never addressed
+        self.Wi = torch.zeros((rows, dim), device=dev)
+        self.bi = torch.zeros(rows, device=dev)
         if init is not None:            # slices of full tables (tests / checkpoints)
             Wu, Wi, bu, bi = init
             self.Wu = Wu[ulo:uhi].clone().to(dev)
-            self.Wi = Wi[ilo:ihi].clone().to(dev)
+            self.Wi[:ihi - ilo] = Wi[ilo:ihi].to(dev)
             self.bu = bu[ulo:uhi].reshape(-1).clone().to(dev)
-            self.bi = bi[ilo:ihi].reshape(-1).clone().to(dev)
+            self.bi[:ihi - ilo] = bi[ilo:ihi].reshape(-1).to(dev)
         else:
             self.Wu = torch.randn((uhi - ulo, dim), device=dev) / dim
-            self.Wi = torch.randn((ihi - ilo, dim), device=dev) / dim
+            self.Wi[:ihi - ilo] = torch.randn((ihi - ilo, dim), device=dev) / dim
             self.bu = torch.zeros(uhi - ulo, device=dev)
-            self.bi = torch.zeros(ihi - ilo, device=dev)
         self.sWu, self.sWi = torch.zeros_like(self.Wu), torch.zeros_like(self.Wi)
         self.sbu, self.sbi = torch.zeros_like(self.bu), torch.zeros_like(self.bi)
 
@@ -313,10 +336,7 @@ class ShardedMF(object):
         plan, st, P = self.plan, self.st, self.plan.world
         chunk, D = plan.ichunk, st.Wi.shape[1]
         dev = users.device
-        pad_W = st.Wi.new_zeros((chunk, D))
-        pad_W[:st.Wi.shape[0]] = st.Wi
-        pad_b = st.bi.new_zeros(chunk)
-        pad_b[:st.bi.shape[0]] = st.bi
+        pad_W, pad_b = st.Wi, st.bi          # shards are stored padded to the common chunk
         full_W = st.Wi.new_empty((P * chunk, D))
         full_b = st.bi.new_empty(P * chunk)
         dist.all_gather_into_tensor(full_W, pad_W, group=self.group)
@@ -616,6 +636,7 @@ class ShardedImplicitFactorizationModel(object):
     def fit(self, interactions, verbose=False):
         be = self.backend
         n = len(interactions.user_ids)
+        trace = _Trace(self.rank)
         if hasattr(be, 'upload_sharded'):
             users_dev = be.upload_sharded(interactions.user_ids, self.rank, self.world, self.mf.group)
             items_dev = be.upload_sharded(interactions.item_ids, self.rank, self.world, self.mf.group)
@@ -624,6 +645,7 @@ class ShardedImplicitFactorizationModel(object):
             items_dev = be.to_device(interactions.item_ids)
         if users_dev.dtype != items_dev.dtype:
             users_dev, items_dev = users_dev.long(), items_dev.long()
+        trace('upload')
         if n:
             umax, imax = torch.stack([users_dev.max(), items_dev.max()]).tolist()      # one sync
             if umax >= self._num_users:
@@ -631,11 +653,15 @@ class ShardedImplicitFactorizationModel(object):
             if imax >= self._num_items:
                 raise ValueError('Maximum item id greater than number of items in model.')
         for epoch in range(self._n_iter):
+            trace('check')
             order = be.shuffled_order(n, self._random_state)
+            trace('shuffle')
             u, i = be.permute(order, users_dev, items_dev)
             del order
+            trace('permute')
             epoch_loss = self._run_epoch_device(u, i)
             del u, i
+            trace('epoch')
             self.epoch_losses.append(epoch_loss)
             if verbose and self.rank == 0:
                 print('Epoch {}: loss {}'.format(epoch, epoch_loss))
@@ -656,6 +682,10 @@ class ShardedImplicitFactorizationModel(object):
         mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
         edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
         bounds = torch.searchsorted(mine, edges).tolist()                   # the epoch's one sync
+        dense = self._exchange == 'dense' or (self._exchange == 'auto' and
+                                              self.mf._dense_exchange_pays(B // plan.world))
+        if dense and nn == 1 and isinstance(be, GpuBackend):
+            return self._epoch_dense_gpu(u, i, mine, bounds)
         mu, mi = u[mine], i[mine]
         bpos = mine % B
         sampler = (be.epoch_sampler(self._num_items, self._random_state, n * nn)
@@ -684,3 +714,124 @@ class ShardedImplicitFactorizationModel(object):
             k, cur = hi_k, min(2 * cur, chunk_batches)
         sampler.finish()
         return float(torch.stack(losses).mean()) if losses else 0.0
+
+    # ------------------------------------------------------------------ fast path
+    def _buffers(self, key, make):
+        cache = self.__dict__.setdefault('_buf_cache', {})
+        if key not in cache:
+            cache[key] = make()
+        return cache[key]
+
+    def _epoch_dense_gpu(self, u, i, mine, bounds, chunk_batches=16):
+        """Whole-shard exchange epoch on the product kernels with nothing but launches on the
+        host side of the loop: per global minibatch k
+
+          plan stream   gather this rank's members (one kernel), integer plan of the local step
+                        (csrc/mf_v2.cuh) -- one step ahead, double buffered
+          main stream   all-gather of the item shards -> mf_user_kernel (user rows updated in
+                        place) -> mf_item_kernel (dense item gradient) -> reduce-scatter ->
+                        Adagrad on the owned shard
+
+        The global negative stream is drawn on the sampler's side stream in chunks; the loss
+        shares are all-reduced once per epoch.  Same arithmetic as ShardedMF.step_dense.
+        """
+        from spotlight_b200.factorization.implicit import _plan_stream
+        lib = _lib.load()
+        be, st, plan, P = self.backend, self.state, self.plan, self.plan.world
+        dev = u.device
+        B, n = self._batch_size, u.numel()
+        nsteps = len(bounds) - 1
+        D, chunk = st.Wi.shape[1], plan.ichunk
+        main, pstream = torch.cuda.current_stream(dev), _plan_stream(dev)
+        loss_kind = _lib.LOSS_KIND[self._loss]
+        maxm = max(1, max(bounds[k + 1] - bounds[k] for k in range(nsteps)))
+        cap = 1 << (maxm - 1).bit_length()                    # capacity bucket: buffers are reused across epochs
+        buf = self._buffers(('dense', cap), lambda: dict(
+            full_W=torch.empty((P * chunk, D), device=dev), full_b=torch.empty(P * chunk, device=dev),
+            dW=torch.empty((P * chunk, D), device=dev), db=torch.empty(P * chunk, device=dev),
+            gW=torch.empty((chunk, D), device=dev), gb=torch.empty(chunk, device=dev),
+            ids=[[torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(3)] for _ in range(2)]))
+        U_sh, I_all = st.Wu.shape[0], P * chunk
+        fws = ops.workspace('mfv2_%d_%d_%d' % (U_sh, I_all, D), lib.slb_mf_fused_workspace_bytes(cap, U_sh, I_all, D), dev)
+        ws = ops.workspace('mf%d_%d' % (U_sh, I_all), lib.slb_mf_step_workspace_bytes(cap, 1, loss_kind, U_sh, I_all), dev)
+        assert fws.numel() > 0, 'planned step unavailable for dim %d' % D
+        losses = torch.zeros(nsteps, dtype=torch.float32, device=dev)
+        sampler = be.epoch_sampler(self._num_items, self._random_state, n)
+        waits = []                                             # (first step, event) per chunk of negatives
+        k, cur = 0, 1
+        while k < nsteps:
+            hi_k = min(k + cur, nsteps)
+            _, ev = sampler.draw(min(hi_k * B, n) - k * B)
+            waits.append((k, ev))
+            k, cur = hi_k, min(2 * cur, chunk_batches)
+        negs_all = sampler.out
+        plan_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        pstream.wait_stream(main)                              # ids, tables and buffers are ready
+        args = [None, None]
+        next_wait = [0]
+
+        def make_args(k):
+            slot = k & 1
+            m = bounds[k + 1] - bounds[k]
+            ul, it, ng = buf['ids'][slot]
+            a = ops.mf_step_args(st.Wu, buf['full_W'], st.bu, buf['full_b'], ul, it, ng, loss_kind, 1, batch=m)
+            a.loss_out = losses[k:k + 1].data_ptr()
+            a.grad_mode = _lib.GRAD_DENSE
+            a.dWi, a.dbi = buf['dW'].data_ptr(), buf['db'].data_ptr()
+            a.opt, a.lr, a.weight_decay, a.eps = _lib.OPT_ADAGRAD, st.lr, 0.0, st.eps
+            a.state_Wu, a.state_bu = st.sWu.data_ptr(), st.sbu.data_ptr()
+            a.norm_batch, a.opt_users_only = int(min(B, n - k * B)), 1
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
+            return a
+
+        def prep(k):
+            slot = k & 1
+            m = bounds[k + 1] - bounds[k]
+            with torch.cuda.stream(pstream):
+                while next_wait[0] < len(waits) and waits[next_wait[0]][0] <= k:
+                    pstream.wait_event(waits[next_wait[0]][1])
+                    next_wait[0] += 1
+                if k >= 2:
+                    pstream.wait_event(done_ev[slot])          # the slot's ids / plan are free again
+                args[slot] = make_args(k)
+                if m:
+                    ul, it, ng = buf['ids'][slot]
+                    _lib.check(lib.slb_shard_gather_batch(
+                        ops._ptr(mine[bounds[k]:]), m, ops._ptr(u), ops._ptr(i), ops._ptr(negs_all), 0, 1,
+                        st.ulo, ops._ptr(ul), ops._ptr(it), ops._ptr(ng), ops._stream()), 'shard_gather_batch')
+                    _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(args[slot]), 1 | (slot << 8),
+                                                            ops._stream()), 'plan')
+                plan_ev[slot].record(pstream)
+
+        prep(0)
+        for k in range(nsteps):
+            if k + 1 < nsteps:
+                prep(k + 1)
+            slot = k & 1
+            m = bounds[k + 1] - bounds[k]
+            dist.all_gather_into_tensor(buf['full_W'], st.Wi, group=self.mf.group)
+            dist.all_gather_into_tensor(buf['full_b'], st.bi, group=self.mf.group)
+            buf['dW'].zero_()
+            buf['db'].zero_()
+            main.wait_event(plan_ev[slot])
+            if m:
+                _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(args[slot]), 6 | (slot << 8),
+                                                        ops._stream()), 'step')
+            done_ev[slot].record(main)
+            dist.reduce_scatter_tensor(buf['gW'], buf['dW'], group=self.mf.group)
+            dist.reduce_scatter_tensor(buf['gb'], buf['db'], group=self.mf.group)
+            _lib.check(lib.slb_adagrad_dense(ops._ptr(st.Wi), ops._ptr(st.sWi), ops._ptr(buf['gW']), chunk * D,
+                                             st.lr, st.eps, ops._stream()), 'adagrad')
+            _lib.check(lib.slb_adagrad_dense(ops._ptr(st.bi), ops._ptr(st.sbi), ops._ptr(buf['gb']), chunk,
+                                             st.lr, st.eps, ops._stream()), 'adagrad')
+            self.mf.stats['bytes_a2a'] += 2 * (buf['full_W'].numel() + buf['full_b'].numel()) * 4
+            self.mf.stats['rows_requested'] += P * chunk
+        pstream.wait_stream(main)                              # later plan-stream work follows this epoch
+        dist.all_reduce(losses, group=self.mf.group)           # one reduction per epoch: global minibatch losses
+        sampler.finish()
+        host = losses.cpu().numpy().astype(np.float64)
+        if ops.workspace_error_flag(ws):
+            raise ValueError('ids out of range reached the device kernels')
+        return float(host.mean()) if nsteps else 0.0

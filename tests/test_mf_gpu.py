@@ -408,7 +408,7 @@ def test_planned_epoch_full_size_two_streams():
     a.grad_mode = _lib.GRAD_COMPACT
     a.opt, a.lr, a.weight_decay, a.eps = _lib.OPT_ADAGRAD, 0.05, 0.0, 1e-10
     a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [x.data_ptr() for x in s2]
-    fws = ops.workspace('mfv2_%d_%d_%d_%d' % (U, I, D, B), lib.slb_mf_fused_workspace_bytes(B, U, I, D), d)
+    fws = ops.workspace('mfv2_%d_%d_%d' % (U, I, D), lib.slb_mf_fused_workspace_bytes(B, U, I, D), d)
     a.fused_workspace, a.fused_workspace_bytes = fws.data_ptr(), fws.numel()
     ws = ops.workspace('mf%d_%d' % (U, I), lib.slb_mf_step_workspace_bytes(B, 1, 1, U, I), d)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()

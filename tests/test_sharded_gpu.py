@@ -253,7 +253,11 @@ def test_sharded_fit_equals_single_gpu_fit(world, loss, exchange):
     -> same final tables, same final generator state."""
     got, losses, state = _results(world)[0]['fit', loss, exchange]
     ref, single_losses, want = _single_gpu_fit(loss)
-    assert_close(np.array(losses), np.array(single_losses), 2e-5, what='epoch losses')
+    # adaptive hinge across ranks: the owners sum their peers' gradient rows in rank order, a
+    # different (equally valid) fp32 order than one GPU's -- exactly the kind of 1e-7 perturbation
+    # that this trajectory amplifies (see below; the oracle's own epoch losses move 1.7e-5 under it)
+    loss_tol = 1e-4 if (loss == 'adaptive_hinge' and world > 1) else 2e-5
+    assert_close(np.array(losses), np.array(single_losses), loss_tol, what='epoch losses')
     for a, b, nm in zip(got, ref, ['Wu', 'Wi', 'bu', 'bi']):
         if loss == 'adaptive_hinge':
             # This trajectory is chaotic at the row level: in the float64 oracle a 1e-7 relative
