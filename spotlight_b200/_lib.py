@@ -19,7 +19,7 @@ c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
 
 LOSS_KIND = {'pointwise': 0, 'bpr': 1, 'hinge': 2, 'adaptive_hinge': 3}
 GRAD_DENSE, GRAD_COMPACT = 0, 1
-OPT_NONE, OPT_SGD, OPT_ADAGRAD = 0, 1, 2
+OPT_NONE, OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2, 3
 
 # every symbol include/spotlight_b200.h declares
 EXPORTS = (
@@ -31,7 +31,7 @@ EXPORTS = (
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
-    'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events',
+    'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events', 'slb_adam_flush',
     'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
     'slb_unique_workspace_bytes', 'slb_unique_bucket', 'slb_shard_gather_batch', 'slb_adagrad_dense',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
@@ -57,6 +57,9 @@ class MfStepArgs(ctypes.Structure):
         ('norm_batch', c_i64), ('opt_users_only', c_i32),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
         ('fused_workspace', c_vp), ('fused_workspace_bytes', c_sz), ('plan_stream', c_vp),
+        ('beta1', c_f32), ('beta2', c_f32), ('one_minus_beta1', c_f32), ('one_minus_beta2', c_f32),
+        ('state2_Wu', c_vp), ('state2_Wi', c_vp), ('state2_bu', c_vp), ('state2_bi', c_vp),
+        ('last_u', c_vp), ('last_i', c_vp), ('adam_sched', c_vp), ('adam_step', c_i64),
     ]
 
 
@@ -137,6 +140,8 @@ def _declare(lib):
     lib.slb_mf_bloom_train_step.argtypes = [P(MfBloomArgs), c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
     lib.slb_mf_fit_epoch_events.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32]
+    lib.slb_adam_flush.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64,
+                                   c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]
     lib.slb_unique_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.slb_unique_workspace_bytes.restype = c_sz
     lib.slb_unique_bucket.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]

@@ -786,6 +786,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
 constexpr int MF_MAX_GRID = 148 * 16;
 
 #include "mf_v2.cuh"
+#include "mf_adam.cuh"
 
 template <int LPR>
 __global__ void __launch_bounds__(MF_THREADS)
@@ -1049,7 +1050,13 @@ int validate(const slb_mf_step_args* x) {
         SLB_REQUIRE(v2_eligible(x) || (x->urows && x->gWu && x->gbu && x->irows && x->gWi && x->gbi && x->compact_counts),
                     "mf_train_step: compact mode needs urows/gWu/gbu/irows/gWi/gbi/compact_counts");
     }
-    SLB_REQUIRE(x->opt >= SLB_OPT_NONE && x->opt <= SLB_OPT_ADAGRAD, "mf_train_step: bad optimizer");
+    SLB_REQUIRE(x->opt >= SLB_OPT_NONE && x->opt <= SLB_OPT_ADAM, "mf_train_step: bad optimizer");
+    if (x->opt == SLB_OPT_ADAM) {
+        SLB_REQUIRE(x->grad_mode == SLB_GRAD_COMPACT && !x->opt_users_only, "mf_train_step: fused Adam needs compact grads");
+        SLB_REQUIRE(x->state_Wu && x->state_Wi && x->state_bu && x->state_bi && x->state2_Wu && x->state2_Wi &&
+                    x->state2_bu && x->state2_bi && x->last_u && x->last_i && x->adam_sched && x->adam_step >= 1,
+                    "mf_train_step: fused Adam needs exp_avg / exp_avg_sq / last / schedule and adam_step >= 1");
+    }
     if (x->opt == SLB_OPT_ADAGRAD) {
         SLB_REQUIRE(x->state_Wu && x->state_bu, "mf_train_step: adagrad needs state");
         SLB_REQUIRE(x->opt_users_only || (x->state_Wi && x->state_bi), "mf_train_step: adagrad needs item state");
@@ -1064,7 +1071,7 @@ int validate(const slb_mf_step_args* x) {
 
 int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* items,
                 const int64_t* negs, int64_t B, float* loss_out, cudaStream_t st,
-                int phases = 0x1f) {
+                int phases = 0x1f, int64_t step_idx = 0) {
     // layout is sized for x->batch so that short last batches reuse the same carve
     MfLayout l = mf_layout(x->workspace, x->batch, x->num_users, x->num_items);
     MfDev a;
@@ -1092,6 +1099,17 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
     int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 8 ? want : static_cast<int64_t>(sms) * 8);
     if (grid < 1) grid = 1;
     if (grid > MF_MAX_GRID) grid = MF_MAX_GRID;
+    if ((phases & 1) && x->opt == SLB_OPT_ADAM) {
+        // lazy-exact Adam: the rows this minibatch reads become current (through step t-1) first
+        AdamDev o = {x->beta1, x->beta2, x->one_minus_beta1, x->one_minus_beta2, x->eps, x->weight_decay, x->adam_sched,
+                     static_cast<int32_t>(x->adam_step + step_idx)};
+        const int64_t refs = (2 + x->n_neg) * B;
+        const int64_t pw = (refs + groups - 1) / groups;
+        const int pgrid = static_cast<int>(pw < static_cast<int64_t>(sms) * 8 ? (pw < 1 ? 1 : pw) : static_cast<int64_t>(sms) * 8);
+        DISPATCH_LPR(lpr, mf_adam_prepass_kernel, pgrid, MF_THREADS, st, a, o, x->state2_Wu, x->state2_Wi,
+                     x->state2_bu, x->state2_bi, x->last_u, x->last_i);
+        SLB_LAUNCH_CHECK("mf_adam_prepass_kernel");
+    }
     if (phases & 1) {
         if (x->loss == SLB_LOSS_ADAPTIVE_HINGE) {
             DISPATCH_LPR(lpr, mf_fwd_kernel, grid, MF_THREADS, st, a);
@@ -1135,12 +1153,20 @@ int launch_step(const slb_mf_step_args* x, const int64_t* users, const int64_t* 
 #define BWD_TILE(MODE)                                                                               \
     if (bsmall) { DISPATCH_LPR3(blpr, mf_bwd_tile_kernel, MODE, 8, tgrid, MF_TILE_THREADS, st, a); } \
     else { DISPATCH_LPR3(blpr, mf_bwd_tile_kernel, MODE, 32, tgrid, MF_TILE_THREADS, st, a); }
-    if (x->opt == SLB_OPT_NONE) {
+    if (x->opt == SLB_OPT_NONE || x->opt == SLB_OPT_ADAM) {
         if (phases & 8) {
             BWD_TILE(0);
             SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
             launch_long<0>(lpr, st, a);
             SLB_LAUNCH_CHECK("mf_bwd_long_kernel");
+        }
+        if (x->opt == SLB_OPT_ADAM && (phases & 16)) {
+            // lazy-exact Adam on the touched rows (mf_adam.cuh): a.sW* hold exp_avg
+            AdamDev o = {x->beta1, x->beta2, x->one_minus_beta1, x->one_minus_beta2, x->eps, x->weight_decay, x->adam_sched,
+                         static_cast<int32_t>(x->adam_step + step_idx)};
+            DISPATCH_LPR(lpr, mf_adam_apply_kernel, bgrid, MF_THREADS, st, a, o, x->state2_Wu, x->state2_Wi,
+                         x->state2_bu, x->state2_bi, x->last_u, x->last_i);
+            SLB_LAUNCH_CHECK("mf_adam_apply_kernel");
         }
     } else {
         // fused optimizer: item gradients first (they read the old user rows), then
@@ -1233,6 +1259,7 @@ bool v2_dim_ok(int D) { return D == 8 || D == 16 || D == 32 || D == 64 || D == 1
 
 bool v2_eligible(const slb_mf_step_args* x) {
     if (x->fused_workspace == nullptr || x->loss == SLB_LOSS_ADAPTIVE_HINGE || x->opt == SLB_OPT_NONE ||
+        x->opt == SLB_OPT_ADAM ||
         !v2_dim_ok(x->dim) || x->pos_out != nullptr || x->neg_out != nullptr)
         return false;
     // single GPU: both tables updated in place (compact mode, nothing materialised); sharded item
@@ -1281,8 +1308,11 @@ template <int LPR, int LOSS>
 void v2_user_launch(const MfDev& a, const PlanDev& p, const StepV2& v, bool small, int grid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(256 / LPR) * (LPR * 4 + 4) * sizeof(float);
     mf_user_long_kernel<LPR, LOSS><<<SEG_LONG_CTAS * 4, 256, smem, st>>>(a, p, v);
-    if (small) mf_user_kernel<LPR, LOSS, 8><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
-    else mf_user_kernel<LPR, LOSS, 32><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
+    if (small) mf_user_kernel<LPR, 1, LOSS, 8><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
+    else if (V2_UVPL == 2 && LPR >= 16) {
+        // the BASELINE dims (64, 128): two 128-bit pieces per lane, half the lanes per row
+        mf_user_kernel<LPR / 2, 2, LOSS, 32><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
+    } else mf_user_kernel<LPR, 1, LOSS, 32><<<grid, MF_TILE_THREADS, 0, st>>>(a, p, v, SEG_LONG_CTAS * 4);
 }
 
 template <int LPR>
@@ -1488,7 +1518,7 @@ static int fit_epoch_impl(const slb_mf_step_args* x, const int64_t* users, const
         // adaptive hinge: negatives of step k are the flat [B*n_neg] block the
         // reference's per-batch randint would have produced (implicit.py:256-259)
         const int64_t* ng = negs + lo * x->n_neg;
-        const int r = launch_step(x, users + lo, items + lo, ng, B, losses_out + step, main_st);
+        const int r = launch_step(x, users + lo, items + lo, ng, B, losses_out + step, main_st, 0x1f, step);
         if (r != SLB_OK) return r;
     }
     return SLB_OK;
@@ -1506,6 +1536,26 @@ int slb_mf_fit_epoch_events(const slb_mf_step_args* x, const int64_t* users, con
     for (int32_t k = 1; k < n_waits; ++k)
         SLB_REQUIRE(wait_steps[k] >= wait_steps[k - 1], "mf_fit_epoch_events: wait_steps must ascend");
     return fit_epoch_impl(x, users, items, negs, n, losses_out, stream, wait_steps, wait_events, n_waits);
+}
+
+int slb_adam_flush(float* W, float* exp_avg, float* exp_avg_sq, float* bias, float* bias_avg, float* bias_avg_sq,
+                   int32_t* last, int64_t rows, int32_t dim, const float* sched, int64_t step,
+                   float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                   float weight_decay, slb_stream_t stream) {
+    SLB_REQUIRE(W && exp_avg && exp_avg_sq && bias && bias_avg && bias_avg_sq && last && sched, "adam_flush: null pointer");
+    SLB_REQUIRE(rows > 0 && dim >= 4 && dim % 4 == 0 && step >= 0 && step < (1ll << 31), "adam_flush: bad sizes");
+    if (step == 0) return SLB_OK;
+    AdamDev o = {beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, sched, static_cast<int32_t>(step)};
+    const int lpr = lpr_for_dim(dim);
+    const int groups = MF_THREADS / lpr;
+    const int64_t want = (rows + groups - 1) / groups;
+    const int sms = slb_sms();
+    const int grid = static_cast<int>(want < static_cast<int64_t>(sms) * 16 ? want : static_cast<int64_t>(sms) * 16);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_LPR(lpr, adam_flush_kernel, grid, MF_THREADS, st, W, exp_avg, exp_avg_sq, bias, bias_avg, bias_avg_sq,
+                 last, rows, dim, o);
+    SLB_LAUNCH_CHECK("adam_flush_kernel");
+    return SLB_OK;
 }
 
 int slb_mf_scores(const float* Wu, const float* Wi, const float* bu, const float* bi,

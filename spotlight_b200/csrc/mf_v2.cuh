@@ -267,20 +267,57 @@ __device__ __forceinline__ void bias_update(const OptV2& o, float* bw, float* bs
 #ifndef V2_UMINB
 #define V2_UMINB 8
 #endif
+#ifndef V2_UMINB2
+#define V2_UMINB2 6
+#endif
+#ifndef V2_UVPL
+#define V2_UVPL 2
+#endif
 #ifndef V2_UPF
 #define V2_UPF 0
 #endif
+
+// A lane holds VPL 128-bit pieces of a row: columns gl*4 + v*LPR*4 (every load of a group covers
+// whole 128-byte lines).  VPL = 2 halves the lanes per row, so a warp iteration carries twice the
+// segments -- twice the bytes in flight per warp, one shuffle level less per reduction.
+template <int VPL>
+struct RowV { float4 v[VPL]; };
+
+template <int LPR, int VPL>
+__device__ __forceinline__ RowV<VPL> row_ldg(const float* row, int gl) {
+    RowV<VPL> r;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) r.v[q] = ldg4(row + gl * 4 + q * LPR * 4);
+    return r;
+}
+template <int LPR, int VPL>
+__device__ __forceinline__ RowV<VPL> row_ldcs(const float* row, int gl) {
+    RowV<VPL> r;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) r.v[q] = __ldcs(reinterpret_cast<const float4*>(row + gl * 4 + q * LPR * 4));
+    return r;
+}
+template <int VPL>
+__device__ __forceinline__ RowV<VPL> row_zero() {
+    RowV<VPL> r;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) r.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
 
 // One interaction of a user segment: two dots, loss, d loss / d score, gradient accumulation.
 // FULL: the whole warp is converged on this call (every group runs it), so the group reductions
 // shuffle under the constant full mask -- plain SHFL.BFLY, no per-shuffle WARPSYNC / MATCH
 // sequence that a run-time group mask compiles to.
-template <int LPR, int LOSS, bool FULL>
-__device__ __forceinline__ void user_member(const float4& w4, float ub, const float4& qi, const float4& qj,
+template <int LPR, int VPL, int LOSS, bool FULL>
+__device__ __forceinline__ void user_member(const RowV<VPL>& w, float ub, const RowV<VPL>& qi, const RowV<VPL>& qj,
                                             float bi_, float bj_, int b, float invB, unsigned gmask, int gl,
-                                            float* t_g, float4& acc, float& bacc, bool& nz, float& lsum) {
-    const float dp = group_sum<LPR>(dot4(w4, qi), FULL ? 0xffffffffu : gmask);
-    const float dn = group_sum<LPR>(dot4(w4, qj), FULL ? 0xffffffffu : gmask);
+                                            float* t_g, RowV<VPL>& acc, float& bacc, bool& nz, float& lsum) {
+    float dp = 0.f, dn = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) { dp += dot4(w.v[q], qi.v[q]); dn += dot4(w.v[q], qj.v[q]); }
+    dp = group_sum<LPR>(dp, FULL ? 0xffffffffu : gmask);
+    dn = group_sum<LPR>(dn, FULL ? 0xffffffffu : gmask);
     float per, gp, gn;
     pair_loss(LOSS, dp + ub + bi_, dn + ub + bj_, per, gp, gn);
     gp *= invB; gn *= invB;
@@ -288,8 +325,8 @@ __device__ __forceinline__ void user_member(const float4& w4, float ub, const fl
         lsum += per;
         *reinterpret_cast<float2*>(t_g + 2 * static_cast<int64_t>(b)) = make_float2(gp, gn);
     }
-    fma4(acc, gp, qi);
-    fma4(acc, gn, qj);
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) { fma4(acc.v[q], gp, qi.v[q]); fma4(acc.v[q], gn, qj.v[q]); }
     bacc += gp + gn;
     nz = nz || gp != 0.f || gn != 0.f;
 }
@@ -297,20 +334,26 @@ __device__ __forceinline__ void user_member(const float4& w4, float ub, const fl
 // Stash the pre-update row for the item side, apply the optimizer in place.  The weight and
 // state rows stream through (evict-first loads / stores): they are touched once per step,
 // while the stash is re-read by mf_item_kernel and the item table by every other segment.
+template <int LPR, int VPL>
 __device__ __forceinline__ void user_finish(const MfDev& a, const OptV2& o, float* stash_row, float* wrow, float* srow,
-                                            float4 w4, float4 s4, const float4& acc, float bacc, bool nz, int row, int gl) {
-    st4(stash_row, w4);
+                                            RowV<VPL> w, RowV<VPL> s, const RowV<VPL>& acc, float bacc, bool nz,
+                                            int row, int gl) {
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) st4(stash_row + gl * 4 + q * LPR * 4, w.v[q]);
     if (nz) {                                        // all-zero gradients leave the row untouched
-        row_update(o, w4, s4, acc);
-        __stcs(reinterpret_cast<float4*>(wrow), w4);
-        if (srow) __stcs(reinterpret_cast<float4*>(srow), s4);
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+            row_update(o, w.v[q], s.v[q], acc.v[q]);
+            __stcs(reinterpret_cast<float4*>(wrow + gl * 4 + q * LPR * 4), w.v[q]);
+            if (srow) __stcs(reinterpret_cast<float4*>(srow + gl * 4 + q * LPR * 4), s.v[q]);
+        }
         if (gl == 0) bias_update(o, a.bu + row, a.sbu ? a.sbu + row : nullptr, bacc);
     }
 }
 
-template <int LPR, int LOSS, int TI>
-__global__ void __launch_bounds__(MF_TILE_THREADS, V2_UMINB) mf_user_kernel(MfDev a, PlanDev p, StepV2 v, int n_long_partials) {
-    constexpr int D = LPR * 4;
+template <int LPR, int VPL, int LOSS, int TI>
+__global__ void __launch_bounds__(MF_TILE_THREADS, (VPL == 1 ? V2_UMINB : V2_UMINB2)) mf_user_kernel(MfDev a, PlanDev p, StepV2 v, int n_long_partials) {
+    constexpr int D = LPR * 4 * VPL;
     constexpr int GPW = 32 / LPR;
     constexpr int WARPS = MF_TILE_THREADS / 32;
     __shared__ float sh_red[WARPS];
@@ -320,7 +363,6 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, V2_UMINB) mf_user_kernel(MfDe
     const int warp = threadIdx.x >> 5;
     const int gl = lane & (LPR - 1);
     const int grp = lane / LPR;
-    const int c = gl * 4;
     const unsigned gmask = group_mask(LPR);
     const unsigned below = (1u << lane) - 1u;
     const float invB = 1.0f / static_cast<float>(a.NB);
@@ -375,56 +417,56 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, V2_UMINB) mf_user_kernel(MfDe
             const int i0 = __shfl_sync(0xffffffffu, r0.y, src);
             const int j0 = __shfl_sync(0xffffffffu, r0.z, src);
             const int s = tile * TI + src;
-            float* wrow = a.Wu + static_cast<int64_t>(s_row) * D + c;
-            float* srow = adagrad ? a.sWu + static_cast<int64_t>(s_row) * D + c : nullptr;
-            float* stash_row = v.stash + static_cast<int64_t>(s) * D + c;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* wrow = a.Wu + static_cast<int64_t>(s_row) * D;
+            float* srow = adagrad ? a.sWu + static_cast<int64_t>(s_row) * D : nullptr;
+            float* stash_row = v.stash + static_cast<int64_t>(s) * D;
+            RowV<VPL> acc = row_zero<VPL>();
             float bacc = 0.f;
             bool nz = false;
             if (q0 + GPW <= n1) {
                 // ---- every group of the warp: one interaction
-                const float4 w4 = __ldcs(reinterpret_cast<const float4*>(wrow));
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (adagrad) s4 = __ldcs(reinterpret_cast<const float4*>(srow));
-                const float4 qi = ldg4(a.Wi + static_cast<int64_t>(i0) * D + c);
-                const float4 qj = ldg4(a.Wi + static_cast<int64_t>(j0) * D + c);
+                const RowV<VPL> w = row_ldcs<LPR, VPL>(wrow, gl);
+                RowV<VPL> st_ = row_zero<VPL>();
+                if (adagrad) st_ = row_ldcs<LPR, VPL>(srow, gl);
+                const RowV<VPL> qi = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(i0) * D, gl);
+                const RowV<VPL> qj = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(j0) * D, gl);
                 const float ub = a.bu[s_row], bi_ = __ldg(a.bi + i0), bj_ = __ldg(a.bi + j0);
-                user_member<LPR, LOSS, true>(w4, ub, qi, qj, bi_, bj_, b0, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
-                user_finish(a, o, stash_row, wrow, srow, w4, s4, acc, bacc, nz, s_row, gl);
+                user_member<LPR, VPL, LOSS, true>(w, ub, qi, qj, bi_, bj_, b0, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
+                user_finish<LPR, VPL>(a, o, stash_row, wrow, srow, w, st_, acc, bacc, nz, s_row, gl);
             } else if (q0 >= n1 && q0 + GPW <= n1 + n2) {
                 // ---- every group of the warp: two interactions
                 const int b1 = __shfl_sync(0xffffffffu, r1.x, src);
                 const int i1 = __shfl_sync(0xffffffffu, r1.y, src);
                 const int j1 = __shfl_sync(0xffffffffu, r1.z, src);
-                const float4 w4 = __ldcs(reinterpret_cast<const float4*>(wrow));
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (adagrad) s4 = __ldcs(reinterpret_cast<const float4*>(srow));
-                const float4 qi0 = ldg4(a.Wi + static_cast<int64_t>(i0) * D + c);
-                const float4 qj0 = ldg4(a.Wi + static_cast<int64_t>(j0) * D + c);
-                const float4 qi1 = ldg4(a.Wi + static_cast<int64_t>(i1) * D + c);
-                const float4 qj1 = ldg4(a.Wi + static_cast<int64_t>(j1) * D + c);
+                const RowV<VPL> w = row_ldcs<LPR, VPL>(wrow, gl);
+                RowV<VPL> st_ = row_zero<VPL>();
+                if (adagrad) st_ = row_ldcs<LPR, VPL>(srow, gl);
+                const RowV<VPL> qi0 = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(i0) * D, gl);
+                const RowV<VPL> qj0 = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(j0) * D, gl);
                 const float ub = a.bu[s_row];
                 const float bi0 = __ldg(a.bi + i0), bj0 = __ldg(a.bi + j0), bi1 = __ldg(a.bi + i1), bj1 = __ldg(a.bi + j1);
-                user_member<LPR, LOSS, true>(w4, ub, qi0, qj0, bi0, bj0, b0, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
-                user_member<LPR, LOSS, true>(w4, ub, qi1, qj1, bi1, bj1, b1, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
-                user_finish(a, o, stash_row, wrow, srow, w4, s4, acc, bacc, nz, s_row, gl);
+                user_member<LPR, VPL, LOSS, true>(w, ub, qi0, qj0, bi0, bj0, b0, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
+                const RowV<VPL> qi1 = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(i1) * D, gl);
+                const RowV<VPL> qj1 = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(j1) * D, gl);
+                user_member<LPR, VPL, LOSS, true>(w, ub, qi1, qj1, bi1, bj1, b1, invB, gmask, gl, v.t_g, acc, bacc, nz, lsum);
+                user_finish<LPR, VPL>(a, o, stash_row, wrow, srow, w, st_, acc, bacc, nz, s_row, gl);
             } else {
                 // ---- mixed iteration (class boundaries, lists of 3+): group-divergent generic path
                 const int s_start = __shfl_sync(0xffffffffu, start, src);
                 if (q >= nvalid || s_len > cap) continue;         // idle group / hot row (mf_user_long_kernel)
-                const float4 w4 = __ldcs(reinterpret_cast<const float4*>(wrow));
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (adagrad) s4 = __ldcs(reinterpret_cast<const float4*>(srow));
+                const RowV<VPL> w = row_ldcs<LPR, VPL>(wrow, gl);
+                RowV<VPL> st_ = row_zero<VPL>();
+                if (adagrad) st_ = row_ldcs<LPR, VPL>(srow, gl);
                 const float ub = a.bu[s_row];
                 for (int k = 0; k < s_len; ++k) {
                     // every lane of the group reads the same (sorted) record: one broadcast transaction
                     const int4 r = __ldg(reinterpret_cast<const int4*>(p.mu + s_start + k));
-                    const float4 qi = ldg4(a.Wi + static_cast<int64_t>(r.y) * D + c);
-                    const float4 qj = ldg4(a.Wi + static_cast<int64_t>(r.z) * D + c);
-                    user_member<LPR, LOSS, false>(w4, ub, qi, qj, __ldg(a.bi + r.y), __ldg(a.bi + r.z), r.x, invB, gmask, gl,
-                                           v.t_g, acc, bacc, nz, lsum);
+                    const RowV<VPL> qi = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(r.y) * D, gl);
+                    const RowV<VPL> qj = row_ldg<LPR, VPL>(a.Wi + static_cast<int64_t>(r.z) * D, gl);
+                    user_member<LPR, VPL, LOSS, false>(w, ub, qi, qj, __ldg(a.bi + r.y), __ldg(a.bi + r.z), r.x, invB, gmask,
+                                                       gl, v.t_g, acc, bacc, nz, lsum);
                 }
-                user_finish(a, o, stash_row, wrow, srow, w4, s4, acc, bacc, nz, s_row, gl);
+                user_finish<LPR, VPL>(a, o, stash_row, wrow, srow, w, st_, acc, bacc, nz, s_row, gl);
             }
         }
     }

@@ -154,8 +154,15 @@ class ImplicitFactorizationModel(object):
                                         sparse=self._sparse), self._use_cuda)
 
         if self._optimizer_func is None:
-            self._optimizer = optim.Adam(self._net.parameters(), weight_decay=self._l2,
-                                         lr=self._learning_rate)
+            if isinstance(self._net, BilinearNet) and self._net.plain_tables() and not self._sparse:
+                # the reference's default, optim.Adam(weight_decay=l2, lr) (implicit.py:143-148), as
+                # the row-wise lazy-exact Adam: same trajectory, O(batch) instead of O(table) per step
+                from spotlight_b200.optim import FusedAdam
+                self._optimizer = FusedAdam(self._net.parameters(), weight_decay=self._l2,
+                                            lr=self._learning_rate)
+            else:
+                self._optimizer = optim.Adam(self._net.parameters(), weight_decay=self._l2,
+                                             lr=self._learning_rate)
         else:
             self._optimizer = self._optimizer_func(self._net.parameters())
 
@@ -282,6 +289,8 @@ class ImplicitFactorizationModel(object):
 
             if np.isnan(epoch_loss) or epoch_loss == 0.0:
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
+        if hasattr(self._optimizer, 'flush'):
+            self._optimizer.flush()             # lazy-exact Adam: every row current before fit() returns
 
     def _run_epoch_device(self, users, items, chunk_batches=48, after_sampling=None):
         """The epoch pipeline over device-resident (already shuffled) ids.
@@ -355,7 +364,7 @@ class ImplicitFactorizationModel(object):
             # planned two-kernel step (plan + user kernel + item kernel, csrc/mf_v2.cuh) whenever the
             # library supports the shape; otherwise the first-generation step with compact gradients
             fused_need = 0
-            if self._loss != 'adaptive_hinge' and PLANNED_STEP:
+            if self._loss != 'adaptive_hinge' and PLANNED_STEP and opt.fused_kind != _lib.OPT_ADAM:
                 fused_need = lib.slb_mf_fused_workspace_bytes(a.batch, a.num_users, a.num_items, a.dim)
             if fused_need:
                 fws = ops.workspace('mfv2_%d_%d_%d' % (a.num_users, a.num_items, a.dim),
@@ -380,9 +389,20 @@ class ImplicitFactorizationModel(object):
                 keep = (urows, irows, gWu, gWi, gbu, gbi, counts)
             hp = opt.fused_hparams()
             a.opt, a.lr, a.weight_decay, a.eps = opt.fused_kind, hp['lr'], hp['weight_decay'], hp['eps']
+            n_steps = (n + B - 1) // B
             if opt.fused_kind == _lib.OPT_ADAGRAD:
                 states = [opt.fused_state(p) for p in (Wu, Wi, bu, bi)]
                 a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [s.data_ptr() for s in states]
+            elif opt.fused_kind == _lib.OPT_ADAM:
+                states = [opt.fused_states(p) for p in (Wu, Wi, bu, bi)]
+                a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [s[0].data_ptr() for s in states]
+                a.state2_Wu, a.state2_Wi, a.state2_bu, a.state2_bi = [s[1].data_ptr() for s in states]
+                a.last_u, a.last_i = states[0][2].data_ptr(), states[1][2].data_ptr()
+                a.beta1, a.beta2 = hp['beta1'], hp['beta2']
+                a.one_minus_beta1, a.one_minus_beta2 = 1.0 - hp['beta1'], 1.0 - hp['beta2']
+                sched = opt.schedule(opt.steps_taken + n_steps, dev)
+                a.adam_sched, a.adam_step = sched.data_ptr(), opt.steps_taken + 1
+                opt.advance(n_steps)
             need = lib.slb_mf_step_workspace_bytes(a.batch, n_neg, a.loss, a.num_users, a.num_items)
             ws = ops.workspace('mf%d_%d' % (a.num_users, a.num_items), need, dev)
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
