@@ -30,7 +30,7 @@ EXPORTS = (
     'slb_shuffle_workspace_bytes', 'slb_shuffle_order', 'slb_permute_ids',
     'slb_embedding_forward', 'slb_bloom_rows',
     'slb_embedding_backward_workspace_bytes', 'slb_embedding_backward',
-    'slb_mf_scores', 'slb_mf_scores_backward', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
+    'slb_mf_scores', 'slb_mf_scores_backward', 'slb_rank_pairs', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
     'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events', 'slb_adam_flush',
     'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
     'slb_unique_workspace_bytes', 'slb_unique_bucket', 'slb_shard_gather_batch', 'slb_adagrad_dense',
@@ -127,6 +127,7 @@ def _declare(lib):
     lib.slb_mf_scores.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]
     lib.slb_mf_scores_backward.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32,
                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.slb_rank_pairs.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]
     lib.slb_mf_step_workspace_bytes.argtypes = [c_i64, c_i32, c_i32, c_i64, c_i64]
     lib.slb_mf_step_workspace_bytes.restype = c_sz
     lib.slb_mf_fused_workspace_bytes.argtypes = [c_i64, c_i64, c_i64, c_i32]

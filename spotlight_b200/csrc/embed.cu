@@ -247,4 +247,43 @@ int slb_embedding_backward(const float* dout, const int64_t* ids, int64_t n, int
     return SLB_OK;
 }
 
+// f3 evaluation scoring: average rank (scipy.stats.rankdata of the NEGATED scores, as
+// spotlight/evaluation.py:49 uses it) of selected items within their user's score row:
+//   rank = 1 + #(scores > s) + 0.5 * (#(scores == s) - 1).
+// One warp per (row, item) pair; the row is L2 resident between the pairs of one user.
+static __global__ void __launch_bounds__(256)
+rank_pairs_kernel(const float* __restrict__ scores, int64_t n_items, const int64_t* __restrict__ pair_row,
+                  const int64_t* __restrict__ pair_item, int64_t n_pairs, float* __restrict__ ranks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n_pairs; p += nwarps) {
+        const float* row = scores + pair_row[p] * n_items;
+        const float s = row[pair_item[p]];
+        int gt = 0, eq = 0;
+        for (int64_t k = lane; k < n_items; k += 32) {
+            const float v = __ldg(row + k);
+            gt += v > s;
+            eq += v == s;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gt += __shfl_xor_sync(0xffffffffu, gt, o);
+            eq += __shfl_xor_sync(0xffffffffu, eq, o);
+        }
+        if (lane == 0) ranks[p] = 1.0f + static_cast<float>(gt) + 0.5f * static_cast<float>(eq - 1);
+    }
+}
+
+int slb_rank_pairs(const float* scores, int64_t n_rows, int64_t n_items, const int64_t* pair_row,
+                   const int64_t* pair_item, int64_t n_pairs, float* ranks, slb_stream_t stream) {
+    if (n_pairs <= 0) return SLB_OK;
+    SLB_REQUIRE(scores && pair_row && pair_item && ranks && n_rows > 0 && n_items > 0, "rank_pairs: bad arguments");
+    const int64_t want = (n_pairs * 32 + 255) / 256;
+    const int grid = static_cast<int>(want < static_cast<int64_t>(slb_sms()) * 16 ? want : static_cast<int64_t>(slb_sms()) * 16);
+    rank_pairs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, n_items, pair_row, pair_item, n_pairs, ranks);
+    SLB_LAUNCH_CHECK("rank_pairs_kernel");
+    return SLB_OK;
+}
+
 }  // extern "C"

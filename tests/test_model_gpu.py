@@ -154,3 +154,92 @@ def test_errors_match_reference():
     bigger = Interactions(np.arange(20, dtype=np.int32), np.arange(20, dtype=np.int32))
     with pytest.raises(ValueError):
         model.fit(bigger)
+
+
+def test_lazy_adam_state_after_every_step():
+    """Step by step: after each minibatch the first moment of every touched row (users and items)
+    equals that of a float64 dense Adam driven by the oracle's gradients -- including rows that
+    missed steps (their pending steps are replayed BEFORE the forward pass, so the scores of
+    step t see the weights dense Adam would have at step t - 1)."""
+    from oracle import mf as omf
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    from spotlight_b200.interactions import Interactions
+    nsteps, U, I, D, B = 6, 400, 90, 32, 128
+    rs = np.random.RandomState(3)
+    n = B * nsteps
+    users = rs.randint(0, U, n).astype(np.int64)
+    items = rs.randint(0, I, n).astype(np.int64)
+    inter = Interactions(users.astype(np.int32), items.astype(np.int32), num_users=U, num_items=I)
+    m = ImplicitFactorizationModel(loss='bpr', embedding_dim=D, n_iter=1, batch_size=B, use_cuda=True,
+                                   random_state=np.random.RandomState(11))
+    m._initialize(inter)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for p in m._net.parameters():
+            p.copy_(torch.randn_like(p) * 0.03)
+    net = m._net
+    P = [p.detach().cpu().numpy().astype(np.float64) for p in
+         (net.user_embeddings.weight, net.item_embeddings.weight, net.user_biases.weight, net.item_biases.weight)]
+    m._random_state = np.random.RandomState(77)
+    negs = np.random.RandomState(77).randint(0, I, n, dtype=np.int64)
+    M = [np.zeros_like(p) for p in P]
+    V = [np.zeros_like(p) for p in P]
+    ud, idv = torch.from_numpy(users).cuda(), torch.from_numpy(items).cuda()
+    gaps = set()
+    last = {0: np.zeros(U, int), 1: np.zeros(I, int)}
+    for t in range(1, nsteps + 1):
+        sl = slice((t - 1) * B, t * B)
+        m._run_epoch_device(ud[sl], idv[sl])                   # one optimizer step, no flush
+        g = omf.mf_step(P[0], P[1], P[2], P[3], users[sl], items[sl], negs[sl], 'bpr', 1, np.float64)
+        for k, gr in enumerate((g['dWu'], g['dWi'], g['dbu'], g['dbi'])):
+            gr = gr.reshape(P[k].shape)
+            M[k] += (gr - M[k]) * 0.1
+            V[k] = V[k] * 0.999 + 0.001 * gr * gr
+            P[k] -= (1e-2 / (1 - 0.9 ** t)) * (M[k] / (np.sqrt(V[k]) / np.sqrt(1 - 0.999 ** t) + 1e-8))
+        for k, prm, ids in ((0, net.user_embeddings.weight, users[sl]),
+                            (1, net.item_embeddings.weight, np.concatenate([items[sl], negs[sl]]))):
+            rows = np.unique(ids)
+            got = m._optimizer.state[prm]['exp_avg'].cpu().numpy()[rows]
+            rel = np.abs(got - M[k][rows]).max(1) / np.abs(M[k][rows]).max(1)
+            assert rel.max() < 1e-4, (t, k, float(rel.max()))
+            assert_close(prm.detach().cpu().numpy()[rows], P[k][rows], 1e-5, what='weights step %d' % t)
+            gaps |= set((t - last[k][rows]).tolist())
+            last[k][rows] = t
+    assert max(gaps) >= 3                                      # rows that missed several steps were exercised
+
+
+@pytest.mark.parametrize('with_train', [False, True])
+def test_mrr_score_blocked_equals_reference_loop(with_train):
+    """spotlight_b200.evaluation.mrr_score (user-block GEMM + slb_rank_pairs) against the
+    reference's own loop (evaluation.py:38-55: per-user predict, FLOAT_MAX on train items,
+    scipy.stats.rankdata), ties included."""
+    import scipy.stats as st
+    from spotlight_b200 import optim
+    from spotlight_b200.evaluation import FLOAT_MAX, mrr_score
+    from spotlight_b200.factorization.implicit import ImplicitFactorizationModel
+    from spotlight_b200.interactions import Interactions
+    rs = np.random.RandomState(1)
+    U, I = 300, 120
+    train = Interactions(rs.randint(0, U, 4000).astype(np.int32), rs.randint(0, I, 4000).astype(np.int32),
+                         num_users=U, num_items=I)
+    test = Interactions(rs.randint(0, U, 700).astype(np.int32), rs.randint(0, I, 700).astype(np.int32),
+                        num_users=U, num_items=I)
+    model = ImplicitFactorizationModel(loss='bpr', embedding_dim=16, n_iter=2, batch_size=256, use_cuda=True,
+                                       optimizer_func=optim.fused_adagrad(lr=0.05),
+                                       random_state=np.random.RandomState(2))
+    model.fit(train)
+    with torch.no_grad():                       # exact ties: two identical item rows
+        model._net.item_embeddings.weight[7] = model._net.item_embeddings.weight[3]
+        model._net.item_biases.weight[7] = model._net.item_biases.weight[3]
+    got = mrr_score(model, test, train if with_train else None, user_block=64)
+    tcsr, trcsr = test.tocsr(), train.tocsr()
+    want = []
+    for user_id, row in enumerate(tcsr):
+        if not len(row.indices):
+            continue
+        predictions = -model.predict(user_id)
+        if with_train:
+            predictions[trcsr[user_id].indices] = FLOAT_MAX
+        want.append((1.0 / st.rankdata(predictions)[row.indices]).mean())
+    assert got.shape == (len(want),)
+    assert_close(got, np.array(want), 1e-6, what='mrr')
