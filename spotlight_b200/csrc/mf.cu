@@ -480,7 +480,12 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
             const bool sA = s < nsegA;
             const float* ptab = sA ? a.Wi : a.Wu;
             const int64_t orow = sA ? s_row : s_row - a.U;
-            if (orow == (sA ? a.frozen_a : a.frozen_b)) continue;     // padding row: no gradient
+            if (orow == (sA ? a.frozen_a : a.frozen_b)) {              // padding row: no gradient
+                if (MODE != 2 && gl == 0 && a.grad_mode == SLB_GRAD_COMPACT) {
+                    if (sA) a.urows[s] = -1; else a.irows[s - nsegA] = -1;      // compact slot unused
+                }
+                continue;
+            }
             if (s_len > CAP) continue;                                 // hot row: mf_bwd_long_kernel
             float* out = nullptr;
             if (MODE != 2) {
@@ -576,6 +581,9 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
                 }
             }
             if (n_gen) __syncwarp(gmask);        // scratch is reused by the next segment
+            if (gl == 0 && MODE != 2 && a.grad_mode == SLB_GRAD_COMPACT) {
+                if (sA) a.urows[s] = orow; else a.irows[s - nsegA] = orow;      // also for hashed tables (no_bias)
+            }
             if (gl == 0 && !a.no_bias) {
                 if (MODE == 2) {
                     float* bw = a.bu + orow;
@@ -591,8 +599,7 @@ __global__ void __launch_bounds__(MF_TILE_THREADS, MODE == 1 ? BWD_MINB1 : BWD_M
                 } else if (a.grad_mode == SLB_GRAD_DENSE) {
                     if (sA) a.dbu[orow] = bacc; else a.dbi[orow] = bacc;
                 } else {
-                    if (sA) { a.urows[s] = orow; a.gbu[s] = bacc; }
-                    else { a.irows[s - nsegA] = orow; a.gbi[s - nsegA] = bacc; }
+                    if (sA) a.gbu[s] = bacc; else a.gbi[s - nsegA] = bacc;
                 }
             }
         }
@@ -627,7 +634,12 @@ __global__ void __launch_bounds__(256) mf_bwd_long_kernel(MfDev a) {
         const int len = a.seg.seg_start[s + 1] - start;
         const int row = a.seg.seg_row[s];
         const int64_t orow = sA ? row : row - a.U;
-        if (orow == (sA ? a.frozen_a : a.frozen_b)) continue;
+        if (orow == (sA ? a.frozen_a : a.frozen_b)) {
+            if (MODE != 2 && threadIdx.x == 0 && a.grad_mode == SLB_GRAD_COMPACT) {
+                if (sA) a.urows[s] = -1; else a.irows[s - nsegA] = -1;
+            }
+            continue;
+        }
         const float* ptab = sA ? a.Wi : a.Wu;
         const int32_t* pidx = sA ? a.t_b : a.t_a;
         const int chunk = (len + GROUPS - 1) / GROUPS;
@@ -692,6 +704,9 @@ __global__ void __launch_bounds__(256) mf_bwd_long_kernel(MfDev a) {
                     st4(out + c, acc);
                 }
             }
+            if (gl == 0 && MODE != 2 && a.grad_mode == SLB_GRAD_COMPACT) {
+                if (sA) a.urows[s] = orow; else a.irows[s - nsegA] = orow;
+            }
             if (gl == 0 && !a.no_bias) {
                 if (MODE == 2) {
                     float* bw = a.bu + orow;
@@ -707,8 +722,7 @@ __global__ void __launch_bounds__(256) mf_bwd_long_kernel(MfDev a) {
                 } else if (a.grad_mode == SLB_GRAD_DENSE) {
                     if (sA) a.dbu[orow] = bacc; else a.dbi[orow] = bacc;
                 } else {
-                    if (sA) { a.urows[s] = orow; a.gbu[s] = bacc; }
-                    else { a.irows[s - nsegA] = orow; a.gbi[s - nsegA] = bacc; }
+                    if (sA) a.gbu[s] = bacc; else a.gbi[s - nsegA] = bacc;
                 }
             }
         }
@@ -745,6 +759,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
         const bool isA = s < nsegA;
         const int64_t k = isA ? s : s - nsegA;
         const int64_t row = isA ? a.urows[k] : a.irows[k];
+        if (row < 0) continue;                                       // frozen (padding) row: slot unused
         float* W = (isA ? a.Wu : a.Wi) + row * D;
         const float* G = (isA ? a.gWu : a.gWi) + k * D;
         float* S = a.opt == SLB_OPT_ADAGRAD ? (isA ? a.sWu : a.sWi) + row * D : nullptr;
@@ -768,7 +783,7 @@ __global__ void __launch_bounds__(MF_THREADS) mf_apply_kernel(MfDev a) {
             }
             st4(W + c, make_float4(wv[0], wv[1], wv[2], wv[3]));
         }
-        if (gl == 0) {
+        if (gl == 0 && !a.no_bias) {
             float* bw = (isA ? a.bu : a.bi) + row;
             float g = (isA ? a.gbu : a.gbi)[k] + a.wd * *bw;
             if (a.opt == SLB_OPT_SGD) {
@@ -1626,11 +1641,111 @@ int slb_mf_scores_backward(const float* gscores, const int64_t* users, const int
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------
+// Sparse update of an id-indexed bias table from n (id, g) pairs -- the unhashed bias tables
+// next to BloomEmbedding layers (representations.py:58-59) have one row per raw id (50 M at
+// BASELINE config 4), so neither a dense gradient nor a scan over the id space is affordable.
+// The pairs are grouped through a hash-bucket segment index (bucket = id & (NB - 1), NB ~ 2n a
+// power of two: count -> scan -> fill), each bucket's few members are ordered by (id, pair) and
+// every distinct id gets its gradient summed in pair order and one optimizer update.
+// Deterministic, O(n) traffic.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct BiasSparse {
+    SegIndex seg;
+    const int64_t* ids; const float* g; int64_t n; int64_t mask;
+    float* b; float* sb;
+    int32_t opt; float lr, wd, eps;
+};
+
+__global__ void __launch_bounds__(256) bias_count_kernel(BiasSparse p) {
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < p.n; k += nth)
+        if (p.g[k] != 0.f) atomicAdd(p.seg.cnt + (p.ids[k] & p.mask), 1);
+}
+
+__global__ void __launch_bounds__(256) bias_fill_kernel(BiasSparse p) {
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < p.n; k += nth)
+        if (p.g[k] != 0.f) seg_place(p.seg, p.ids[k] & p.mask, static_cast<int32_t>(k));
+}
+
+__global__ void __launch_bounds__(256) bias_apply_kernel(BiasSparse p) {
+    const int nseg = p.seg.totals[0];
+    const OptV2 o = {p.opt, p.lr, p.wd, p.eps};
+    const int nth = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += nth) {
+        const int start = p.seg.seg_start[s], len = p.seg.seg_start[s + 1] - start;
+        // members of one bucket: process distinct ids in ascending (id, pair) order by repeated
+        // selection (buckets hold ~1 pair; O(len^2) is irrelevant)
+        int64_t last_id = -1;
+        for (;;) {
+            int64_t cur = INT64_MAX;
+            for (int m = 0; m < len; ++m) {
+                const int64_t id = p.ids[p.seg.members[start + m]];
+                if (id > last_id && id < cur) cur = id;
+            }
+            if (cur == INT64_MAX) break;
+            // sum this id's pairs in ascending pair order
+            float acc = 0.f;
+            int prev = -1;
+            for (;;) {
+                int best = INT32_MAX;
+                for (int m = 0; m < len; ++m) {
+                    const int k = p.seg.members[start + m];
+                    if (k > prev && k < best && p.ids[k] == cur) best = k;
+                }
+                if (best == INT32_MAX) break;
+                acc += p.g[best];
+                prev = best;
+            }
+            bias_update(o, p.b + cur, p.sb ? p.sb + cur : nullptr, acc);
+            last_id = cur;
+        }
+    }
+}
+
+size_t bias_sparse_bytes(int64_t n) {
+    int64_t nb = 4096;
+    while (nb < 2 * n) nb <<= 1;
+    WsCarver ws(nullptr);
+    seg_index_carve(ws, nb, n);
+    return ws.bytes();
+}
+
+int bias_sparse_apply(void* wsp, const int64_t* ids, const float* g, int64_t n, float* b, float* sb,
+                      int32_t opt, float lr, float wd, float eps, cudaStream_t st) {
+    int64_t nb = 4096;
+    while (nb < 2 * n) nb <<= 1;
+    WsCarver ws(wsp);
+    BiasSparse p;
+    p.seg = seg_index_carve(ws, nb, n);
+    p.ids = ids; p.g = g; p.n = n; p.mask = nb - 1; p.b = b; p.sb = sb;
+    p.opt = opt; p.lr = lr; p.wd = wd; p.eps = eps;
+    const int sms = slb_sms();
+    int grid = static_cast<int>((n + 255) / 256);
+    if (grid > sms * 8) grid = sms * 8;
+    bias_count_kernel<<<grid, 256, 0, st>>>(p);
+    SLB_LAUNCH_CHECK("bias_count_kernel");
+    seg_scan_launch(p.seg, p.seg.Rpad, st);
+    SLB_LAUNCH_CHECK("seg_scan_kernel");
+    bias_fill_kernel<<<grid, 256, 0, st>>>(p);
+    SLB_LAUNCH_CHECK("bias_fill_kernel");
+    bias_apply_kernel<<<grid, 256, 0, st>>>(p);
+    SLB_LAUNCH_CHECK("bias_apply_kernel");
+    return SLB_OK;
+}
+
+}  // namespace
+
 struct BloomLayout {
     int32_t* t_a; int32_t* t_b; float* t_g; float* partial; int32_t* done; int32_t* err;
     SegIndex seg;
     int64_t* ids_u2; int64_t* ids_i2; float* g_u2; float* g_i2;
     void* ws_u; size_t ws_u_bytes; void* ws_i; size_t ws_i_bytes;
+    // fused-optimizer mode: compact item-row gradients + hash-bucket bias workspaces
+    int64_t* irows; float* gWi; int32_t* compact_counts; void* bws_u; void* bws_i;
     size_t bytes;
 };
 
@@ -1650,10 +1765,23 @@ static BloomLayout bloom_layout(void* base, const slb_mf_bloom_args* x) {
     l.ids_i2 = ws.take<int64_t>(2 * B);
     l.g_u2 = ws.take<float>(2 * B);
     l.g_i2 = ws.take<float>(2 * B);
-    l.ws_u_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_users);
-    l.ws_u = ws.take<char>(l.ws_u_bytes);
-    l.ws_i_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_items);
-    l.ws_i = ws.take<char>(l.ws_i_bytes);
+    l.irows = nullptr; l.gWi = nullptr; l.compact_counts = nullptr; l.bws_u = nullptr; l.bws_i = nullptr;
+    l.ws_u = nullptr; l.ws_i = nullptr; l.ws_u_bytes = 0; l.ws_i_bytes = 0;
+    if (x->base.opt == SLB_OPT_NONE) {
+        l.ws_u_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_users);
+        l.ws_u = ws.take<char>(l.ws_u_bytes);
+        l.ws_i_bytes = slb_embedding_backward_workspace_bytes(2 * B, x->base.num_items);
+        l.ws_i = ws.take<char>(l.ws_i_bytes);
+    } else {
+        // the two bias workspaces are zero-at-rest and must precede the batch-sized scratch?  No:
+        // this workspace is dedicated to one (shapes, batch), so every offset is fixed.
+        l.bws_u = ws.take<char>(bias_sparse_bytes(2 * B));
+        l.bws_i = ws.take<char>(bias_sparse_bytes(2 * B));
+        const int64_t irow_cap = T < x->item_rows ? T : x->item_rows;
+        l.irows = ws.take<int64_t>(irow_cap + 1);
+        l.gWi = ws.take<float>(static_cast<size_t>(irow_cap + 1) * x->base.dim);
+        l.compact_counts = ws.take<int32_t>(4);
+    }
     l.bytes = ws.bytes();
     return l;
 }
@@ -1671,14 +1799,18 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     SLB_REQUIRE(b.batch > 0 && b.dim >= 4 && b.dim % 4 == 0, "mf_bloom_train_step: bad batch / dim");
     SLB_REQUIRE(b.loss >= 0 && b.loss <= 3 && b.n_neg >= 1, "mf_bloom_train_step: bad loss / n_neg");
     SLB_REQUIRE(b.loss == SLB_LOSS_ADAPTIVE_HINGE || b.n_neg == 1, "mf_bloom_train_step: n_neg > 1 only for adaptive hinge");
-    SLB_REQUIRE(b.grad_mode == SLB_GRAD_DENSE && b.opt == SLB_OPT_NONE, "mf_bloom_train_step: dense gradients, no fused optimizer");
+    const bool fused = b.opt != SLB_OPT_NONE;
+    SLB_REQUIRE(fused ? (b.opt == SLB_OPT_SGD || b.opt == SLB_OPT_ADAGRAD) : b.grad_mode == SLB_GRAD_DENSE,
+                "mf_bloom_train_step: dense gradients, or a fused SGD / Adagrad optimizer");
+    SLB_REQUIRE(!fused || b.opt == SLB_OPT_SGD || (b.state_Wu && b.state_Wi && b.state_bu && b.state_bi),
+                "mf_bloom_train_step: adagrad needs state");
     SLB_REQUIRE(x->user_hashes >= 0 && x->user_hashes <= 24 && x->item_hashes >= 0 && x->item_hashes <= 24,
                 "mf_bloom_train_step: at most 24 hash functions");
     SLB_REQUIRE(x->user_rows > 0 && x->item_rows > 0 && b.num_users > 0 && b.num_items > 0, "mf_bloom_train_step: empty tables");
     SLB_REQUIRE(x->user_hashes > 0 || x->user_rows == b.num_users, "mf_bloom_train_step: plain user table must have num_users rows");
     SLB_REQUIRE(x->item_hashes > 0 || x->item_rows == b.num_items, "mf_bloom_train_step: plain item table must have num_items rows");
-    SLB_REQUIRE(b.users && b.items && b.negs && b.Wu && b.Wi && b.bu && b.bi && b.loss_out && b.dWu && b.dWi && b.dbu && b.dbi && b.workspace,
-                "mf_bloom_train_step: null pointer");
+    SLB_REQUIRE(b.users && b.items && b.negs && b.Wu && b.Wi && b.bu && b.bi && b.loss_out && b.workspace &&
+                (fused || (b.dWu && b.dWi && b.dbu && b.dbi)), "mf_bloom_train_step: null pointer");
     const int nu = x->user_hashes ? x->user_hashes : 1, ni = x->item_hashes ? x->item_hashes : 1;
     const int64_t B = b.batch, T = 2 * B * nu * ni;
     SLB_REQUIRE(x->user_rows + x->item_rows < (1ll << 31) - SEG_SCAN_TILE && 2 * T < (1ll << 31),
@@ -1699,8 +1831,11 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     a.seg = l.seg;
     const int lpr = lpr_for_dim(b.dim);
     a.seg.long_cap = seg_sort_cap(lpr);
-    a.grad_mode = SLB_GRAD_DENSE;
+    a.grad_mode = fused ? SLB_GRAD_COMPACT : SLB_GRAD_DENSE;
     a.dWu = b.dWu; a.dWi = b.dWi; a.dbu = b.dbu; a.dbi = b.dbi;
+    a.irows = l.irows; a.gWi = l.gWi; a.compact_counts = l.compact_counts;
+    a.opt = b.opt; a.lr = b.lr; a.wd = b.weight_decay; a.eps = b.eps;
+    a.sWu = b.state_Wu; a.sWi = b.state_Wi; a.sbu = b.state_bu; a.sbi = b.state_bi;
     a.no_bias = 1;
     a.frozen_a = x->user_hashes ? x->user_padding_idx : -1;
     a.frozen_b = x->item_hashes ? x->item_padding_idx : -1;
@@ -1735,6 +1870,23 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     SLB_LAUNCH_CHECK("seg_sort_long_kernel");
     const int64_t tw = ((2 * T + 31) / 32 + 3) / 4;
     const int tgrid = static_cast<int>(tw < static_cast<int64_t>(sms) * 16 ? tw : static_cast<int64_t>(sms) * 16);
+    if (fused) {
+        // hashed item rows first (compact gradients from the old user rows), user rows updated in
+        // place, item rows updated from the compact gradients, then the id-space biases
+        DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 1, 32, tgrid, MF_TILE_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<items>");
+        launch_long<1>(lpr, st, a);
+        DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 2, 32, tgrid, MF_TILE_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_bwd_tile_kernel<users+opt>");
+        launch_long<2>(lpr, st, a);
+        const int64_t aw = (2 * T + groups - 1) / groups;
+        const int agrid = static_cast<int>(aw < static_cast<int64_t>(sms) * 8 ? aw : static_cast<int64_t>(sms) * 8);
+        DISPATCH_LPR2(lpr, mf_apply_kernel, 1, agrid, MF_THREADS, st, a);
+        SLB_LAUNCH_CHECK("mf_apply_kernel<items>");
+        int rcb = bias_sparse_apply(l.bws_u, l.ids_u2, l.g_u2, 2 * B, b.bu, b.state_bu, b.opt, b.lr, b.weight_decay, b.eps, st);
+        if (rcb != SLB_OK) return rcb;
+        return bias_sparse_apply(l.bws_i, l.ids_i2, l.g_i2, 2 * B, b.bi, b.state_bi, b.opt, b.lr, b.weight_decay, b.eps, st);
+    }
     DISPATCH_LPR3(lpr, mf_bwd_tile_kernel, 0, 32, tgrid, MF_TILE_THREADS, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     launch_long<0>(lpr, st, a);

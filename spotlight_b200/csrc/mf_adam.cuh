@@ -110,6 +110,7 @@ mf_adam_apply_kernel(MfDev a, AdamDev o, float* vWu, float* vWi, float* vbu, flo
         const bool isA = s < nsegA;
         const int64_t k = isA ? s : s - nsegA;
         const int64_t row = isA ? a.urows[k] : a.irows[k];
+        if (row < 0) continue;
         float* W = (isA ? a.Wu : a.Wi) + row * D;
         float* M = (isA ? a.sWu : a.sWi) + row * D;
         float* V = (isA ? vWu : vWi) + row * D;

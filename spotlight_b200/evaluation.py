@@ -46,7 +46,7 @@ def mrr_score(model, test, train=None, user_block=2048):
             tr = train[blk]
             rows = np.repeat(np.arange(len(blk)), np.diff(tr.indptr))
             if len(rows):
-                scores[torch.from_numpy(rows).to(dev), torch.from_numpy(tr.indices.astype(np.int64)).to(dev)] = -FLOAT_MAX
+                scores[torch.from_numpy(rows).to(dev), torch.from_numpy(tr.indices.astype(np.int64)).to(dev)] = -float(FLOAT_MAX)
         te = test[blk]
         n_per = np.diff(te.indptr)
         pair_row = torch.from_numpy(np.repeat(np.arange(len(blk)), n_per).astype(np.int64)).to(dev)

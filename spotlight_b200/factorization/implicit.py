@@ -279,6 +279,9 @@ class ImplicitFactorizationModel(object):
                             pending = (shuffle_begin(n, self._random_state, device), side)
                 epoch_loss = self._run_epoch_device(user_ids_tensor, item_ids_tensor,
                                                     after_sampling=next_permutation)
+            elif route == 'bloom' and getattr(self._optimizer, 'fused_kind', None) in (_lib.OPT_SGD, _lib.OPT_ADAGRAD):
+                negatives = self._epoch_negatives(len(user_ids))
+                epoch_loss = self._fit_epoch_bloom_fused(user_ids_tensor, item_ids_tensor, negatives)
             else:
                 negatives = self._epoch_negatives(len(user_ids))
                 epoch_loss = self._fit_epoch_autograd(user_ids_tensor, item_ids_tensor, negatives,
@@ -422,6 +425,28 @@ class ImplicitFactorizationModel(object):
             if ops.workspace_error_flag(ws):
                 raise ValueError('ids out of range reached the device kernels')
         return float(host.sum() / n_steps)
+
+    def _fit_epoch_bloom_fused(self, users, items, negatives):
+        """Hashed-table model with a fused row-wise optimizer: one in-place step per minibatch
+        (csrc/mf.cu slb_mf_bloom_train_step, fused mode), no dense gradient of any table."""
+        net, opt = self._net, self._optimizer
+        spec = net.fused_spec()
+        n_neg = self._n_neg()
+        hp = opt.fused_hparams()
+        params = (spec['Wu'], spec['Wi'], net.user_biases.weight, net.item_biases.weight)
+        states = [opt.fused_state(p) for p in params] if opt.fused_kind == _lib.OPT_ADAGRAD else None
+        losses = []
+        lo = 0
+        for batch_user, batch_item in minibatch(users, items, batch_size=self._batch_size):
+            B = batch_user.numel()
+            batch_neg = negatives[lo * n_neg:(lo + B) * n_neg]
+            lo += B
+            losses.append(ops.mf_bloom_train_step_inplace(
+                *params, batch_user, batch_item, batch_neg, self._loss, n_neg, spec['user_seeds'],
+                spec['item_seeds'], spec['user_pad'], spec['item_pad'], opt.fused_kind, hp['lr'], states,
+                hp['weight_decay'], hp['eps']))
+        host = torch.stack(losses).cpu().numpy().astype(np.float64)        # one sync per epoch
+        return float(host.sum() / len(host))
 
     def _fit_epoch_autograd(self, users, items, negatives, fused):
         net = self._net

@@ -398,6 +398,46 @@ def _(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, user_seeds, item_seeds, u
             torch.empty_like(Wu), torch.empty_like(Wi), torch.empty_like(bu), torch.empty_like(bi))
 
 
+def mf_bloom_train_step_inplace(Wu, Wi, bu, bi, users, items, negs, loss, n_neg, user_seeds, item_seeds,
+                                user_pad, item_pad, opt_kind, lr, states=None, weight_decay=0.0, eps=1e-10):
+    """The fused hashed-table step with the row-wise optimizer applied in place: hashed / plain
+    embedding rows through the compact-gradient kernels, the id-indexed bias tables through the
+    hash-bucket sparse update (no dense gradient anywhere -- the item-bias table of BASELINE
+    config 4 has 50 M rows).  ``states`` = (sWu, sWi, sbu, sbi) for Adagrad.  Returns the loss."""
+    require_cuda(Wu, Wi, bu, bi, users, items, negs)
+    lib = _lib.load()
+    users, items, negs = _i64c(users).reshape(-1), _i64c(items).reshape(-1), _i64c(negs).reshape(-1)
+    B = users.numel()
+    dev = Wu.device
+    with torch.no_grad():
+        x = MfBloomArgs()
+        a = x.base
+        a.batch = B
+        a.users, a.items, a.negs = users.data_ptr(), items.data_ptr(), negs.data_ptr()
+        a.loss, a.n_neg = (LOSS_KIND[loss] if isinstance(loss, str) else int(loss)), int(n_neg)
+        a.num_users, a.num_items, a.dim = bu.shape[0], bi.shape[0], Wu.shape[1]
+        a.Wu, a.Wi, a.bu, a.bi = Wu.data_ptr(), Wi.data_ptr(), bu.data_ptr(), bi.data_ptr()
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+        a.loss_out = loss_out.data_ptr()
+        a.grad_mode = _lib.GRAD_COMPACT
+        a.opt, a.lr, a.weight_decay, a.eps = int(opt_kind), float(lr), float(weight_decay), float(eps)
+        if opt_kind == _lib.OPT_ADAGRAD:
+            a.state_Wu, a.state_Wi, a.state_bu, a.state_bi = [t.data_ptr() for t in states]
+        x.user_rows, x.item_rows = Wu.shape[0], Wi.shape[0]
+        x.user_hashes, x.item_hashes = len(user_seeds), len(item_seeds)
+        for k, sd in enumerate(user_seeds):
+            x.user_seeds[k] = int(sd) & 0xFFFFFFFF
+        for k, sd in enumerate(item_seeds):
+            x.item_seeds[k] = int(sd) & 0xFFFFFFFF
+        x.user_padding_idx, x.item_padding_idx = user_pad, item_pad
+        need = lib.slb_mf_bloom_workspace_bytes(ctypes.byref(x))
+        ws = workspace('mfbf%d_%d_%d_%d_%d_%d_%d_%d' % (Wu.shape[0], Wi.shape[0], bu.shape[0], bi.shape[0],
+                                                        len(user_seeds), len(item_seeds), B, a.n_neg), need, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.slb_mf_bloom_train_step(ctypes.byref(x), _stream()), 'mf_bloom_train_step')
+    return loss_out.reshape(())
+
+
 class _FusedBloomLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Wu, Wi, bu, bi, users, items, negs, loss, n_neg, us, its, up, ip):

@@ -620,6 +620,62 @@ def test_fused_bloom_step_golden(name, loss):
     assert np.all(dWi[0] == 0)          # the padding row of the compressed table is frozen
 
 
+@pytest.mark.parametrize('name,loss', [('mf_hinge_bloom', 'hinge'), ('mf_adaptive_bloom', 'adaptive_hinge')])
+def test_fused_bloom_inplace_sgd_golden(name, loss):
+    """Hashed-table step with the optimizer fused in (compact row gradients, hash-bucket sparse
+    bias update, nothing dense): one SGD step reproduces W - lr * (the live reference's gradient)."""
+    from spotlight_b200 import _lib, ops
+    from spotlight_b200.layers import SEEDS
+    g = load_golden(name)
+    H = int(g['bloom_H'])
+    n_neg = int(g['n_neg']) if loss == 'adaptive_hinge' else 1
+    names = ['user_embeddings.weight', 'item_embeddings.embeddings.weight', 'user_biases.weight', 'item_biases.weight']
+    grads = [g['grad.' + k] for k in names]
+    lr = 0.3 / max(np.abs(x).max() for x in grads[:2])
+    prm = [t(g['sd.' + k].copy()) for k in names]
+    l = ops.mf_bloom_train_step_inplace(*prm, t(g['users']), t(g['items']), t(g['negs']), loss, n_neg,
+                                        [], SEEDS[:H], -1, 0, _lib.OPT_SGD, lr)
+    assert_close(l.item(), g['loss'], 1e-5, what='loss')
+    for k, p, gr in zip(names, prm, grads):
+        want = g['sd.' + k].astype(np.float64) - lr * gr
+        assert_close(p.cpu().numpy(), want, 5e-6, what=k)
+
+
+def test_fused_bloom_config4_inplace_vs_dense():
+    """BASELINE config 4 shape: the in-place fused step equals the dense-gradient step followed by
+    the same optimizer (SGD tables; Adagrad accumulators = g^2), including the 50 M-row item bias."""
+    from spotlight_b200 import _lib, ops
+    from spotlight_b200.layers import SEEDS
+    torch.manual_seed(4)
+    U, N, M, D, H, B = 1_000_000, 50_000_000, 1_000_000, 64, 4, 65536
+    d = dev()
+    base = [torch.randn(U, D, device=d) / D, torch.randn(M, D, device=d) / D,
+            torch.randn(U, 1, device=d) * 0.01, torch.randn(N, 1, device=d) * 0.01]
+    base[1][0] = 0
+    rs = np.random.RandomState(45)
+    users, items, negs = t(rs.randint(0, U, B).astype(np.int64)), t(rs.randint(1, N, B).astype(np.int64)), \
+        t(rs.randint(0, N, B).astype(np.int64))
+    loss, _, _, dWu, dWi, dbu, dbi = ops.mf_bloom_train_step(*base, users, items, negs, 0, 1, [], SEEDS[:H], -1, 0, False)
+    lr = 0.01 / float(max(dWu.abs().max(), dWi.abs().max()))
+    p1 = [x.clone() for x in base]
+    l1 = ops.mf_bloom_train_step_inplace(*p1, users, items, negs, 'pointwise', 1, [], SEEDS[:H], -1, 0, _lib.OPT_SGD, lr)
+    assert_close(l1.item(), loss.item(), 1e-6, what='loss')
+    for p, b0, gr, nm in zip(p1, base, (dWu, dWi, dbu, dbi), ('Wu', 'Wi', 'bu', 'bi')):
+        assert_close_dev(p, b0 - lr * gr.reshape(b0.shape), 2e-6, what=nm)
+    p2 = [x.clone() for x in base]
+    st = [torch.zeros_like(x) for x in p2]
+    ops.mf_bloom_train_step_inplace(*p2, users, items, negs, 'pointwise', 1, [], SEEDS[:H], -1, 0, _lib.OPT_ADAGRAD,
+                                    0.05, states=st)
+    for s_, gr, nm in zip(st, (dWu, dWi, dbu, dbi), ('sWu', 'sWi', 'sbu', 'sbi')):
+        assert_close_dev(s_, (gr * gr).reshape(s_.shape), 2e-5, atol=1e-30, what=nm)
+    p3 = [x.clone() for x in base]
+    st3 = [torch.zeros_like(x) for x in p3]
+    ops.mf_bloom_train_step_inplace(*p3, users, items, negs, 'pointwise', 1, [], SEEDS[:H], -1, 0, _lib.OPT_ADAGRAD,
+                                    0.05, states=st3)
+    for x, y in zip(p2 + st, p3 + st3):
+        assert torch.equal(x, y), 'fused hashed step is not bit-reproducible'
+
+
 def test_fused_bloom_both_sides_vs_generic_route():
     """Bloom on users *and* items (the reference's own MF Bloom test shape,
     tests/factorization/test_implicit.py:127-164): fused step == generic autograd route."""
