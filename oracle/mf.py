@@ -135,3 +135,35 @@ def mf_step(Wu, Wi, bu, bi, users, items, negs, loss='bpr', n_neg=1,
 def bloom_embed(W, rows):
     """layers.py:240-241: sum of the H hashed rows.  rows: (..., H)."""
     return W[rows].sum(axis=-2)
+
+
+def mf_bloom_step(Wu, Wi, bu, bi, users, items, negs, loss, num_hash, pad=0, dtype=np.float64):
+    """One minibatch of BilinearNet with a BloomEmbedding ITEM layer (plain user table):
+    the item vector is the sum of the H hashed rows (layers.py:206-244), the biases stay
+    indexed by the raw ids (representations.py:58-59).  ``Wi`` is the (M, D) hashed table.
+    Returns loss and dense gradients dWu, dWi (M rows, padding row 0 frozen), dbu, dbi.
+    Non-adaptive losses only (the sharded hashed path, BASELINE config 4, uses hinge)."""
+    from oracle.murmur import bloom_rows
+    M = Wi.shape[0]
+    ri = bloom_rows(np.asarray(items), num_hash, M, pad)
+    rj = bloom_rows(np.asarray(negs), num_hash, M, pad)
+    Wu_, Wi_ = Wu.astype(dtype), Wi.astype(dtype)
+    u = Wu_[users]
+    qi, qj = Wi_[ri].sum(1), Wi_[rj].sum(1)
+    pos = (u * qi).sum(1) + bu.reshape(-1)[users] + bi.reshape(-1)[items]
+    neg = (u * qj).sum(1) + bu.reshape(-1)[users] + bi.reshape(-1)[negs]
+    l, gp, gn = loss_and_score_grads(loss, pos.astype(dtype), neg.astype(dtype), None, dtype)
+    dWu = np.zeros(Wu.shape, dtype=np.float64)
+    dWi = np.zeros(Wi.shape, dtype=np.float64)
+    dbu = np.zeros(bu.shape, dtype=np.float64)
+    dbi = np.zeros(bi.shape, dtype=np.float64)
+    np.add.at(dWu, users, gp[:, None] * qi + gn[:, None] * qj)
+    for k in range(num_hash):
+        np.add.at(dWi, ri[:, k], gp[:, None] * u)
+        np.add.at(dWi, rj[:, k], gn[:, None] * u)
+    dWi[0] = 0                                   # the padding row of the compressed table is frozen
+    np.add.at(dbu.reshape(-1), users, gp + gn)
+    np.add.at(dbi.reshape(-1), items, gp)
+    np.add.at(dbi.reshape(-1), negs, gn)
+    return dict(loss=l, pos=pos, neg=neg, dWu=dWu, dWi=dWi, dbu=dbu, dbi=dbi)
+

@@ -33,6 +33,7 @@ EXPORTS = (
     'slb_mf_scores', 'slb_mf_scores_backward', 'slb_rank_pairs', 'slb_mf_step_workspace_bytes', 'slb_mf_fused_workspace_bytes', 'slb_mf_compact_rows',
     'slb_mf_train_step', 'slb_mf_train_step_phases', 'slb_mf_fit_epoch', 'slb_mf_fit_epoch_events', 'slb_adam_flush',
     'slb_mf_bloom_workspace_bytes', 'slb_mf_bloom_train_step',
+    'slb_bias_sparse_workspace_bytes', 'slb_bias_sparse_apply',
     'slb_unique_workspace_bytes', 'slb_unique_bucket', 'slb_shard_gather_batch', 'slb_adagrad_dense',
     'slb_loss_workspace_bytes', 'slb_pairwise_loss',
     'slb_seq_step_workspace_bytes', 'slb_seq_train_step', 'slb_seq_representation',
@@ -71,6 +72,7 @@ class MfBloomArgs(ctypes.Structure):
         ('user_hashes', c_i32), ('item_hashes', c_i32),
         ('user_seeds', ctypes.c_uint32 * 24), ('item_seeds', ctypes.c_uint32 * 24),
         ('user_padding_idx', c_i64), ('item_padding_idx', c_i64),
+        ('pair_ids_u', c_vp), ('pair_g_u', c_vp), ('pair_ids_i', c_vp), ('pair_g_i', c_vp),
     ]
 
 
@@ -139,6 +141,9 @@ def _declare(lib):
     lib.slb_mf_bloom_workspace_bytes.argtypes = [P(MfBloomArgs)]
     lib.slb_mf_bloom_workspace_bytes.restype = c_sz
     lib.slb_mf_bloom_train_step.argtypes = [P(MfBloomArgs), c_vp]
+    lib.slb_bias_sparse_workspace_bytes.argtypes = [c_i64]
+    lib.slb_bias_sparse_workspace_bytes.restype = c_sz
+    lib.slb_bias_sparse_apply.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_f32, c_f32, c_f32, c_vp, c_sz, c_vp]
     lib.slb_mf_fit_epoch.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
     lib.slb_mf_fit_epoch_events.argtypes = [P(MfStepArgs), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32]
     lib.slb_adam_flush.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64,

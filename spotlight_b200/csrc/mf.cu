@@ -1809,8 +1809,9 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     SLB_REQUIRE(x->user_rows > 0 && x->item_rows > 0 && b.num_users > 0 && b.num_items > 0, "mf_bloom_train_step: empty tables");
     SLB_REQUIRE(x->user_hashes > 0 || x->user_rows == b.num_users, "mf_bloom_train_step: plain user table must have num_users rows");
     SLB_REQUIRE(x->item_hashes > 0 || x->item_rows == b.num_items, "mf_bloom_train_step: plain item table must have num_items rows");
+    const bool pairs_u = x->pair_ids_u && x->pair_g_u, pairs_i = x->pair_ids_i && x->pair_g_i;
     SLB_REQUIRE(b.users && b.items && b.negs && b.Wu && b.Wi && b.bu && b.bi && b.loss_out && b.workspace &&
-                (fused || (b.dWu && b.dWi && b.dbu && b.dbi)), "mf_bloom_train_step: null pointer");
+                (fused || (b.dWu && b.dWi && (b.dbu || pairs_u) && (b.dbi || pairs_i))), "mf_bloom_train_step: null pointer");
     const int nu = x->user_hashes ? x->user_hashes : 1, ni = x->item_hashes ? x->item_hashes : 1;
     const int64_t B = b.batch, T = 2 * B * nu * ni;
     SLB_REQUIRE(x->user_rows + x->item_rows < (1ll << 31) - SEG_SCAN_TILE && 2 * T < (1ll << 31),
@@ -1845,6 +1846,8 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     for (int k = 0; k < 24; ++k) { h.su[k] = x->user_seeds[k]; h.si[k] = x->item_seeds[k]; }
     h.num_users = b.num_users; h.num_items = b.num_items;
     h.ids_u2 = l.ids_u2; h.ids_i2 = l.ids_i2; h.g_u2 = l.g_u2; h.g_i2 = l.g_i2;
+    if (!fused && pairs_u) { h.ids_u2 = x->pair_ids_u; h.g_u2 = x->pair_g_u; }
+    if (!fused && pairs_i) { h.ids_i2 = x->pair_ids_i; h.g_i2 = x->pair_g_i; }
 
     const int groups = MF_THREADS / lpr;
     const int sms = slb_sms();
@@ -1891,13 +1894,33 @@ int slb_mf_bloom_train_step(const slb_mf_bloom_args* x, slb_stream_t stream) {
     SLB_LAUNCH_CHECK("mf_bwd_tile_kernel");
     launch_long<0>(lpr, st, a);
     SLB_LAUNCH_CHECK("mf_bwd_long_kernel");
-    // id-space bias gradients: deterministic scalar scatter (D = 1)
-    int rc = slb_embedding_backward(l.g_u2, l.ids_u2, 2 * B, 0, nullptr, b.num_users, 1, -1, b.dbu, l.ws_u,
+    // id-space bias gradients: deterministic scalar scatter (D = 1), unless handed out as pairs
+    int rc = SLB_OK;
+    if (!pairs_u)
+        rc = slb_embedding_backward(l.g_u2, l.ids_u2, 2 * B, 0, nullptr, b.num_users, 1, -1, b.dbu, l.ws_u,
                                     l.ws_u_bytes, stream);
     if (rc != SLB_OK) return rc;
-    rc = slb_embedding_backward(l.g_i2, l.ids_i2, 2 * B, 0, nullptr, b.num_items, 1, -1, b.dbi, l.ws_i,
-                                l.ws_i_bytes, stream);
+    if (!pairs_i)
+        rc = slb_embedding_backward(l.g_i2, l.ids_i2, 2 * B, 0, nullptr, b.num_items, 1, -1, b.dbi, l.ws_i,
+                                    l.ws_i_bytes, stream);
     return rc;
+}
+
+size_t slb_bias_sparse_workspace_bytes(int64_t n) { return n > 0 ? bias_sparse_bytes(n) : 0; }
+
+int slb_bias_sparse_apply(const int64_t* ids, const float* g, int64_t n, float* bias, float* state,
+                          int32_t opt, float lr, float weight_decay, float eps,
+                          void* workspace, size_t workspace_bytes, slb_stream_t stream) {
+    if (n <= 0) return SLB_OK;
+    SLB_REQUIRE(ids && g && bias && workspace, "bias_sparse_apply: null pointer");
+    SLB_REQUIRE(opt == SLB_OPT_SGD || (opt == SLB_OPT_ADAGRAD && state), "bias_sparse_apply: SGD, or Adagrad with state");
+    SLB_REQUIRE(n < (1ll << 30), "bias_sparse_apply: too many pairs");
+    if (workspace_bytes < bias_sparse_bytes(n)) {
+        slb_set_error("bias_sparse_apply: workspace too small");
+        return SLB_ENOSPC;
+    }
+    return bias_sparse_apply(workspace, ids, g, n, bias, state, opt, lr, weight_decay, eps,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

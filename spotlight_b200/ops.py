@@ -438,6 +438,62 @@ def mf_bloom_train_step_inplace(Wu, Wi, bu, bi, users, items, negs, loss, n_neg,
     return loss_out.reshape(())
 
 
+def mf_bloom_step_pairs(Wu, Wi, bu, bi, users, items, negs, loss, item_seeds, item_pad, norm_batch=0):
+    """Dense-mode hashed-table step for the multi-GPU path: plain (local) user table, hashed item
+    table given in full; returns (loss share, dWu, dWi, (ids_u, g_u), (ids_i, g_i)) -- the
+    id-space bias gradients as (id, g) pairs instead of dense tables."""
+    require_cuda(Wu, Wi, bu, bi, users, items, negs)
+    lib = _lib.load()
+    users, items, negs = _i64c(users).reshape(-1), _i64c(items).reshape(-1), _i64c(negs).reshape(-1)
+    B = users.numel()
+    dev = Wu.device
+    with torch.no_grad():
+        x = MfBloomArgs()
+        a = x.base
+        a.batch = B
+        a.users, a.items, a.negs = users.data_ptr(), items.data_ptr(), negs.data_ptr()
+        a.loss, a.n_neg = (LOSS_KIND[loss] if isinstance(loss, str) else int(loss)), 1
+        a.num_users, a.num_items, a.dim = bu.shape[0], bi.shape[0], Wu.shape[1]
+        a.Wu, a.Wi, a.bu, a.bi = Wu.data_ptr(), Wi.data_ptr(), bu.data_ptr(), bi.data_ptr()
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+        dWu, dWi = torch.zeros_like(Wu), torch.zeros_like(Wi)
+        pu_i = torch.empty(2 * B, dtype=torch.int64, device=dev)
+        pu_g = torch.empty(2 * B, dtype=torch.float32, device=dev)
+        pi_i = torch.empty(2 * B, dtype=torch.int64, device=dev)
+        pi_g = torch.empty(2 * B, dtype=torch.float32, device=dev)
+        a.loss_out = loss_out.data_ptr()
+        a.grad_mode = _lib.GRAD_DENSE
+        a.dWu, a.dWi = dWu.data_ptr(), dWi.data_ptr()
+        a.norm_batch = int(norm_batch)
+        x.pair_ids_u, x.pair_g_u, x.pair_ids_i, x.pair_g_i = pu_i.data_ptr(), pu_g.data_ptr(), pi_i.data_ptr(), pi_g.data_ptr()
+        x.user_rows, x.item_rows = Wu.shape[0], Wi.shape[0]
+        x.user_hashes, x.item_hashes = 0, len(item_seeds)
+        for k, sd in enumerate(item_seeds):
+            x.item_seeds[k] = int(sd) & 0xFFFFFFFF
+        x.user_padding_idx, x.item_padding_idx = -1, item_pad
+        need = lib.slb_mf_bloom_workspace_bytes(ctypes.byref(x))
+        ws = workspace('mfbp%d_%d_%d_%d_%d_%d' % (Wu.shape[0], Wi.shape[0], bu.shape[0], bi.shape[0],
+                                                  len(item_seeds), B), need, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.slb_mf_bloom_train_step(ctypes.byref(x), _stream()), 'mf_bloom_train_step')
+    return loss_out.reshape(()), dWu, dWi, (pu_i, pu_g), (pi_i, pi_g)
+
+
+def bias_sparse_apply(ids, g, bias, state, opt_kind, lr, weight_decay=0.0, eps=1e-10):
+    """In-place SGD / Adagrad update of an id-indexed bias table from (id, g) pairs (g == 0 pairs
+    are padding)."""
+    require_cuda(ids, g, bias)
+    lib = _lib.load()
+    n = ids.numel()
+    if n == 0:
+        return
+    ws = workspace('bsp%d' % n, lib.slb_bias_sparse_workspace_bytes(n), bias.device)
+    with torch.no_grad():
+        _lib.check(lib.slb_bias_sparse_apply(_ptr(_i64c(ids)), _ptr(_f32c(g)), n, _ptr(bias), _ptr(state),
+                                             int(opt_kind), float(lr), float(weight_decay), float(eps),
+                                             _ptr(ws), ws.numel(), _stream()), 'bias_sparse_apply')
+
+
 class _FusedBloomLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Wu, Wi, bu, bi, users, items, negs, loss, n_neg, us, its, up, ip):

@@ -130,6 +130,20 @@ class GpuBackend(object):
         adagrad_dense_(st.bi, st.sbi, db.reshape(-1), st.lr, st.eps)
 
 
+    # ---- hashed item table (BloomEmbedding, config 4) ----
+    def bloom_local_step(self, st, W_full, users_local, items, negs, loss, global_batch):
+        """Dense-mode hashed step on (local user shard, full hashed item table, replicated item
+        bias): returns (loss share, dWu, dWi, user bias pairs, item bias pairs)."""
+        return ops.mf_bloom_step_pairs(st.Wu, W_full, st.bu.reshape(-1, 1), st.bi.reshape(-1, 1), users_local, items,
+                                       negs, loss, st.item_seeds, 0, norm_batch=global_batch)
+
+    def adagrad_dense(self, W, S, G, lr, eps):
+        _lib.check(_lib.load().slb_adagrad_dense(ops._ptr(W), ops._ptr(S), ops._ptr(G.contiguous()), W.numel(),
+                                                 lr, eps, ops._stream()), 'adagrad_dense')
+
+    def bias_sparse_adagrad(self, ids, g, bias, state, lr, eps):
+        ops.bias_sparse_apply(ids, g, bias, state, _lib.OPT_ADAGRAD, lr, 0.0, eps)
+
     # ---- adaptive hinge: scores, loss and score gradients as separate calls ----
     def scores(self, st, cache_rows, cache_bias, u_idx, i_idx):
         return ops.mf_scores(st.Wu, cache_rows, st.bu.reshape(-1, 1), cache_bias.reshape(-1, 1), u_idx, i_idx)
@@ -835,3 +849,98 @@ class ShardedImplicitFactorizationModel(object):
         if ops.workspace_error_flag(ws):
             raise ValueError('ids out of range reached the device kernels')
         return float(host.mean()) if nsteps else 0.0
+
+
+class BloomShardState(object):
+    """Parameters of BilinearNet(plain users, BloomEmbedding items) on one rank: user rows / user
+    bias sharded by user range, the hashed item table (M rows) sharded by row range and padded to
+    the common chunk, the item bias (one float per raw item id) REPLICATED -- its forward lookup
+    needs 2 values per interaction from arbitrary owners, which would cost a host-synchronised
+    all-to-all per step for 4-byte payloads; its replicas are kept identical by applying the same
+    all-gathered sparse updates on every rank."""
+
+    def __init__(self, plan, rank, dim, device, num_ids, hashed_rows, num_hash, lr=0.05, eps=1e-10, init=None):
+        from spotlight_b200.layers import SEEDS
+        dev = torch.device(device)
+        self.lr, self.eps = float(lr), float(eps)
+        self.ulo, self.uhi = plan.user_range(rank)
+        self.M, self.num_ids = int(hashed_rows), int(num_ids)
+        self.mchunk = -(-self.M // plan.world)
+        self.mlo = min(rank * self.mchunk, self.M)
+        self.mhi = min(self.mlo + self.mchunk, self.M)
+        self.item_seeds = [int(x) for x in SEEDS[:num_hash]]
+        self.Wi = torch.zeros((self.mchunk, dim), device=dev)
+        if init is not None:
+            Wu, Wi, bu, bi = init
+            self.Wu = Wu[self.ulo:self.uhi].clone().to(dev)
+            self.bu = bu[self.ulo:self.uhi].reshape(-1).clone().to(dev)
+            self.Wi[:self.mhi - self.mlo] = Wi[self.mlo:self.mhi].to(dev)
+            self.bi = bi.reshape(-1).clone().to(dev)
+        else:
+            self.Wu = torch.randn((self.uhi - self.ulo, dim), device=dev) / dim
+            self.bu = torch.zeros(self.uhi - self.ulo, device=dev)
+            self.Wi[:self.mhi - self.mlo] = torch.randn((self.mhi - self.mlo, dim), device=dev) / dim
+            if self.mlo == 0:
+                self.Wi[0] = 0                      # padding row of the hashed table
+            self.bi = torch.zeros(self.num_ids, device=dev)
+        self.sWu, self.sWi = torch.zeros_like(self.Wu), torch.zeros_like(self.Wi)
+        self.sbu, self.sbi = torch.zeros_like(self.bu), torch.zeros_like(self.bi)
+
+
+class ShardedBloomMF(object):
+    """Training step of the hashed-item model on N ranks (BASELINE config 4:
+    BloomEmbedding 50 M items -> 1 M hashed rows, hinge / bpr / pointwise).
+
+    Interactions are routed to the rank that owns their user (user gathers and updates local).
+    The hashed table is range-sharded; a rank's minibatch references 2 * B * H hashed rows -- at
+    config 4 sizes a large fraction of all M rows -- so the table travels whole: all-gather of the
+    shards, the fused hashed step on the full table (in-register murmur3, layers.py:178-204),
+    reduce-scatter of the dense table gradient to the owners, who apply Adagrad.  The id-space
+    bias gradients travel as (id, g) pairs: all-gather, then the same sparse update on every
+    replica.  Loss: one scalar all-reduce."""
+
+    def __init__(self, plan, state, rank, backend, group=None, pair_capacity=None):
+        self.plan, self.st, self.rank, self.backend, self.group = plan, state, rank, backend, group
+        self.pair_capacity = pair_capacity
+        self.stats = {'bytes_exchanged': 0}
+
+    def step(self, users, items, negs, loss, global_batch):
+        st, P, be = self.st, self.plan.world, self.backend
+        dev = st.Wi.device
+        D = st.Wi.shape[1]
+        W_full = st.Wi.new_empty((P * st.mchunk, D))
+        dist.all_gather_into_tensor(W_full, st.Wi, group=self.group)
+        m = users.numel()
+        cap = self.pair_capacity or 2 * int(global_batch)
+        ids_pad = torch.zeros(cap, dtype=torch.int64, device=dev)
+        g_pad = torch.zeros(cap, dtype=torch.float32, device=dev)
+        if m:
+            loss_share, dWu, dWi, (iu, gu), (ii, gi) = be.bloom_local_step(st, W_full[:st.M], users - st.ulo, items,
+                                                                           negs, loss, global_batch)
+            be.adagrad_dense(st.Wu, st.sWu, dWu, st.lr, st.eps)
+            be.bias_sparse_adagrad(iu, gu, st.bu, st.sbu, st.lr, st.eps)
+            ids_pad[:ii.numel()] = ii
+            g_pad[:gi.numel()] = gi
+            dW_pad = dWi.new_zeros((P * st.mchunk, D))
+            dW_pad[:st.M] = dWi
+        else:
+            loss_share = st.bu.new_zeros(())
+            dW_pad = st.Wi.new_zeros((P * st.mchunk, D))
+        g_shard = st.Wi.new_empty((st.mchunk, D))
+        try:
+            dist.reduce_scatter_tensor(g_shard, dW_pad, group=self.group)
+        except (RuntimeError, NotImplementedError):          # gloo: sum everywhere, keep our slice
+            y = dW_pad.clone()
+            dist.all_reduce(y, group=self.group)
+            g_shard.copy_(y[self.rank * st.mchunk:(self.rank + 1) * st.mchunk])
+        be.adagrad_dense(st.Wi, st.sWi, g_shard, st.lr, st.eps)
+        ids_all = torch.empty(P * cap, dtype=torch.int64, device=dev)
+        g_all = torch.empty(P * cap, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ids_all, ids_pad, group=self.group)
+        dist.all_gather_into_tensor(g_all, g_pad, group=self.group)
+        be.bias_sparse_adagrad(ids_all, g_all, st.bi, st.sbi, st.lr, st.eps)
+        self.stats['bytes_exchanged'] += (W_full.numel() + dW_pad.numel()) * 4 + P * cap * 12
+        total = loss_share.detach().clone().reshape(1)
+        dist.all_reduce(total, group=self.group)
+        return total.reshape(())
+

@@ -39,6 +39,39 @@ class NumpyBackend(object):
                 torch.from_numpy((r['dWi'] * scale).astype(np.float32))[:n_cache],
                 torch.from_numpy((r['dbi'].reshape(-1) * scale).astype(np.float32))[:n_cache])
 
+    # hashed item table (config 4)
+    def bloom_local_step(self, st, W_full, users_local, items, negs, loss, global_batch):
+        H = len(st.item_seeds)
+        B = users_local.numel()
+        r = omf.mf_bloom_step(st.Wu.numpy().astype(np.float64), W_full.numpy().astype(np.float64),
+                              st.bu.numpy().astype(np.float64), st.bi.numpy().astype(np.float64),
+                              users_local.numpy(), items.numpy(), negs.numpy(), loss, H, 0, np.float64)
+        scale = B / float(global_batch)
+        # bias gradients as (id, g) pairs, as the product kernel hands them out; for the oracle the
+        # per-id totals are enough: one pair per touched id
+        def pairs(dense):
+            d = dense.reshape(-1) * scale
+            ids = np.nonzero(d)[0]
+            return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(d[ids].astype(np.float32))
+        f = lambda x: torch.from_numpy((x * scale).astype(np.float32))       # noqa: E731
+        return (torch.tensor(float(r['loss']) * scale, dtype=torch.float32), f(r['dWu']), f(r['dWi']),
+                pairs(r['dbu']), pairs(r['dbi']))
+
+    def adagrad_dense(self, W, S, G, lr, eps):
+        g = G.numpy().astype(np.float64)
+        s = S.numpy().astype(np.float64) + g * g
+        w = W.numpy().astype(np.float64) - lr * g / (np.sqrt(s) + eps)
+        S.copy_(torch.from_numpy(s.astype(np.float32)))
+        W.copy_(torch.from_numpy(w.astype(np.float32)))
+
+    def bias_sparse_adagrad(self, ids, g, bias, state, lr, eps):
+        tot = np.zeros(bias.numel())
+        np.add.at(tot, ids.numpy(), g.numpy().astype(np.float64))
+        s = state.numpy().astype(np.float64) + tot * tot
+        w = bias.numpy().astype(np.float64) - lr * tot / (np.sqrt(s) + eps)
+        state.copy_(torch.from_numpy(s.astype(np.float32)))
+        bias.copy_(torch.from_numpy(w.astype(np.float32)))
+
     # adaptive hinge pieces
     def scores(self, st, cache_rows, cache_bias, u_idx, i_idx):
         Wu, bu = st.Wu.numpy().astype(np.float64), st.bu.numpy().astype(np.float64)
@@ -273,3 +306,54 @@ def sharded_fit_run(rank, world, params, users, items, loss, device, backend, se
                                               num_negative_samples=n_neg)
     model.fit(Interactions(users, items, num_users=U, num_items=I))
     return gather_tables(model.state, model.plan, U, I, world), model.epoch_losses, rs.get_state()
+
+
+# ---------------------------------------------------------------- hashed item table (config 4)
+
+def make_bloom_problem(seed, U, N, M, D, B, steps):
+    rs = np.random.RandomState(seed)
+    Wu = (rs.randn(U, D) * 0.3).astype(np.float32)
+    Wi = (rs.randn(M, D) * 0.3).astype(np.float32)
+    Wi[0] = 0
+    bu = (rs.randn(U, 1) * 0.1).astype(np.float32)
+    bi = (rs.randn(N, 1) * 0.1).astype(np.float32)
+    batches = [(rs.randint(0, U, B).astype(np.int64), rs.randint(1, N, B).astype(np.int64),
+                rs.randint(0, N, B).astype(np.int64)) for _ in range(steps)]
+    return (Wu, Wi, bu, bi), batches
+
+
+def bloom_oracle_run(params, batches, loss, lr, H, eps=1e-10):
+    P = [p.astype(np.float64) for p in params]
+    S = [np.zeros_like(p) for p in P]
+    losses = []
+    for users, items, negs in batches:
+        r = omf.mf_bloom_step(P[0], P[1], P[2], P[3], users, items, negs, loss, H, 0, np.float64)
+        losses.append(float(r['loss']))
+        for k, g in enumerate((r['dWu'], r['dWi'], r['dbu'], r['dbi'])):
+            S[k] += g * g
+            P[k] -= lr * g / (np.sqrt(S[k]) + eps)
+    return P, losses
+
+
+def bloom_sharded_run(rank, world, params, batches, loss, lr, device, backend, H):
+    from spotlight_b200.sharded import BloomShardState, ShardedBloomMF, ShardPlan
+    U, D = params[0].shape
+    M, N = params[1].shape[0], params[3].shape[0]
+    plan = ShardPlan(U, N, world)
+    st = BloomShardState(plan, rank, D, device, N, M, H, lr=lr, init=[torch.from_numpy(p) for p in params])
+    model = ShardedBloomMF(plan, st, rank, backend)
+    losses = []
+    for users, items, negs in batches:
+        mine = plan.user_owner(users) == rank
+        t = lambda x: torch.from_numpy(x[mine]).to(device)        # noqa: E731
+        losses.append(float(model.step(t(users), t(items), t(negs), loss, len(users))))
+    out = []
+    for shard, n, chunk in ((st.Wu, U, plan.uchunk), (st.Wi, M, st.mchunk), (st.bu.reshape(-1, 1), U, plan.uchunk)):
+        pad = torch.zeros((chunk,) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        pad[:shard.shape[0]] = shard
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat(parts)[:n].cpu().numpy())
+    out.append(st.bi.reshape(-1, 1).cpu().numpy())           # replicated
+    return out, losses
+

@@ -169,3 +169,19 @@ def test_parallel_shuffle_formulation_matches_numpy(n):
             probe2.randint(0, 2 ** 32, used, dtype=np.uint64)
         assert np.array_equal(probe2.get_state()[1], rs.get_state()[1])
         assert probe2.get_state()[2] == rs.get_state()[2]
+
+
+def test_oracle_bloom_step_vs_reference_golden():
+    """oracle.mf.mf_bloom_step (hashed item rows summed, raw-id biases) against the gradients the
+    live reference produced for BilinearNet + BloomEmbedding (tests/golden/mf_hinge_bloom.npz)."""
+    from oracle import mf as omf
+    g = load_golden('mf_hinge_bloom')
+    r = omf.mf_bloom_step(g['sd.user_embeddings.weight'], g['sd.item_embeddings.embeddings.weight'],
+                          g['sd.user_biases.weight'], g['sd.item_biases.weight'], g['users'], g['items'],
+                          g['negs'], 'hinge', int(g['bloom_H']), 0, np.float64)
+    assert_close(float(r['loss']), float(g['loss']), 1e-6, what='loss')
+    assert_close(r['pos'], g['pos'], 1e-5, what='pos')
+    for k, nm in (('dWu', 'user_embeddings.weight'), ('dWi', 'item_embeddings.embeddings.weight'),
+                  ('dbu', 'user_biases.weight'), ('dbi', 'item_biases.weight')):
+        assert_close(r[k], g['grad.' + nm], 1e-6, atol=1e-12, what=k)
+

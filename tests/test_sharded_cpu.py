@@ -173,3 +173,46 @@ def test_shard_plan_ranges():
     assert [plan.user_range(r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert [plan.item_range(r) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 7)]
     assert plan.user_owner(torch.tensor([0, 2, 3, 9])).tolist() == [0, 0, 1, 3]
+
+
+BLOOM = (9, 120, 700, 64, 8, 128, 3, 3)         # seed, U, N ids, M hashed rows, D, B, steps, H
+
+
+def _bloom_worker(rank, world, port, loss, q):
+    import sharded_common as sc
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        seed, U, N, M, D, B, steps, H = BLOOM
+        params, batches = sc.make_bloom_problem(seed, U, N, M, D, B, steps)
+        got, losses = sc.bloom_sharded_run(rank, world, params, batches, loss, 0.05, 'cpu', sc.NumpyBackend(), H)
+        if rank == 0:
+            q.put((got, losses))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,loss', [(2, 'bpr'), (3, 'pointwise'), (4, 'bpr')])
+def test_sharded_bloom_step_matches_single_process(world, loss):
+    """BASELINE config 4's partitioning (hashed item rows range-sharded, users owner-routed,
+    id-space item bias replicated through all-gathered sparse updates) against the
+    single-process float64 oracle of BilinearNet + BloomEmbedding."""
+    import sharded_common as sc
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 27500 + (os.getpid() + world * 11) % 2000
+    procs = [ctx.Process(target=_bloom_worker, args=(r, world, port, loss, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, losses = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seed, U, N, M, D, B, steps, H = BLOOM
+    params, batches = sc.make_bloom_problem(seed, U, N, M, D, B, steps)
+    ref, ref_losses = sc.bloom_oracle_run(params, batches, loss, 0.05, H)
+    assert_close(np.array(losses), np.array(ref_losses), 1e-5, what='losses')
+    for a, b, nm in zip(got, ref, ['Wu', 'Wi(hashed)', 'bu', 'bi']):
+        assert_close(a, b.reshape(a.shape), 2e-5, what=nm)
+

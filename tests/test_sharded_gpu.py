@@ -35,6 +35,7 @@ FIT = dict(seed=33, U=3000, I=800, D=32, n=300000, B=16384, n_iter=2)
 FIT_JOBS = [('bpr', 'a2a'), ('bpr', 'dense'), ('adaptive_hinge', 'a2a')]
 
 ADA = dict(seed=19, U=1500, I=400, D=32, B=768, n=4)       # one adaptive-hinge step, gradients
+BLOOM = (9, 3000, 40000, 1500, 32, 2048, 3, 4)            # seed, U, N ids, M hashed rows, D, B, steps, H
 
 
 def _fit_problem():
@@ -112,6 +113,10 @@ def _worker(rank, world, port, q):
             res['fit', loss, exchange] = sc.sharded_fit_run(rank, world, params, users, items, loss, dev,
                                                            GpuBackend(dev), FIT['seed'], FIT['B'],
                                                            FIT['n_iter'], exchange, n_neg=4)
+        seed, U, N, M, D, B, steps, H = BLOOM
+        params, batches = sc.make_bloom_problem(seed, U, N, M, D, B, steps)
+        for loss in ('bpr', 'hinge'):
+            res['bloom', loss] = sc.bloom_sharded_run(rank, world, params, batches, loss, 0.05, dev, GpuBackend(dev), H)
         res['ada', rank] = _adaptive_grad_job(rank, world, dev)
         torch.cuda.synchronize()
         q.put((rank, res, None))
@@ -208,6 +213,24 @@ def test_sharded_adaptive_hinge_step_gradients(world):
     assert_close(dbu, ref['dbu'].reshape(-1), 1e-5, atol=1e-9, what='dbu')
     assert_close(dbi, ref['dbi'].reshape(-1), 1e-5, atol=1e-9, what='dbi')
     assert np.abs(ref['dWi']).max() > 0 and np.abs(ref['dWu']).max() > 0
+
+
+@pytest.mark.parametrize('world', WORLDS)
+@pytest.mark.parametrize('loss', ['bpr', 'hinge'])
+def test_sharded_bloom_gpu_matches_oracle(world, loss):
+    """BASELINE config 4's partitioning on the product kernels (hashed item table range-sharded and
+    exchanged whole, fused hashed step with in-register murmur3, sparse bias updates) against the
+    single-process float64 oracle of BilinearNet + BloomEmbedding."""
+    import sharded_common as sc
+    got, losses = _results(world)[0]['bloom', loss]
+    seed, U, N, M, D, B, steps, H = BLOOM
+    params, batches = sc.make_bloom_problem(seed, U, N, M, D, B, steps)
+    ref, ref_losses = sc.bloom_oracle_run(params, batches, loss, 0.05, H)
+    assert_close(np.array(losses), np.array(ref_losses), 1e-5, what='losses')
+    for a, b, nm in zip(got, ref, ['Wu', 'Wi(hashed)', 'bu', 'bi']):
+        if loss == 'hinge' and nm in ('bu', 'bi'):
+            continue        # +-1/B gradients cancel exactly or leave a 1e-9 residue by summation order: see test_sharded_cpu
+        assert_close(a, b.reshape(a.shape), 5e-3, what=nm)      # Adagrad trajectory tolerance
 
 
 _SINGLE = {}
