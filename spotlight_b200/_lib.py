@@ -90,6 +90,8 @@ class SeqStepArgs(ctypes.Structure):
         ('dE', c_vp), ('dbias', c_vp),
         ('norm_count', c_vp),
         ('workspace', c_vp), ('workspace_bytes', c_sz),
+        ('opt', c_i32), ('lr', c_f32), ('weight_decay', c_f32), ('eps', c_f32),
+        ('state_E', c_vp), ('state_bias', c_vp),
     ]
 
 

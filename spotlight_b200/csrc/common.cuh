@@ -127,4 +127,44 @@ __device__ __forceinline__ int64_t bloom_row(int64_t id, uint32_t seed, int64_t 
     return m;
 }
 
+// ---- row-wise optimizers shared by the MF and sequence kernels --------------------------------
+// Adagrad step  w -= lr * g / (sqrt(s) + eps)  with MUFU-based sqrt and division (rsqrt 2 ulp,
+// fast divide 2 ulp: ~5e-7 relative, far inside the 1e-5 parity budget; the IEEE sqrtf +
+// division pair costs ~20 instructions per element and made the update kernels issue-bound).
+__device__ __forceinline__ float adagrad_delta(float lr, float g, float s, float eps) {
+    const float root = s > 0.f ? s * rsqrtf(s) : 0.f;
+    return __fdividef(lr * g, root + eps);
+}
+
+struct OptV2 { int32_t opt; float lr, wd, eps; };
+
+__device__ __forceinline__ void row_update(const OptV2& o, float4& w, float4& s, const float4& g0) {
+    float gv[4] = {g0.x + o.wd * w.x, g0.y + o.wd * w.y, g0.z + o.wd * w.z, g0.w + o.wd * w.w};
+    float wv[4] = {w.x, w.y, w.z, w.w};
+    if (o.opt == SLB_OPT_SGD) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wv[q] -= o.lr * gv[q];
+    } else {
+        float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sv[q] += gv[q] * gv[q];
+            wv[q] -= adagrad_delta(o.lr, gv[q], sv[q], o.eps);
+        }
+        s = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    }
+    w = make_float4(wv[0], wv[1], wv[2], wv[3]);
+}
+
+__device__ __forceinline__ void bias_update(const OptV2& o, float* bw, float* bs, float g) {
+    const float gb = g + o.wd * *bw;
+    if (o.opt == SLB_OPT_SGD) {
+        *bw -= o.lr * gb;
+    } else {
+        const float sv = *bs + gb * gb;
+        *bs = sv;
+        *bw -= adagrad_delta(o.lr, gb, sv, o.eps);
+    }
+}
+
 #endif  // __CUDACC__

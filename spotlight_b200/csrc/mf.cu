@@ -297,11 +297,6 @@ __global__ void __launch_bounds__(MF_TILE_THREADS) mf_fwd_tile_kernel(MfDev a) {
 // (rsqrt 2 ulp, fast divide 2 ulp: ~5e-7 relative, far inside the 1e-5 parity
 // budget; the IEEE sqrtf + division pair costs ~20 instructions per element and
 // made the update kernel issue-bound).
-__device__ __forceinline__ float adagrad_delta(float lr, float g, float s, float eps) {
-    const float root = s > 0.f ? s * rsqrtf(s) : 0.f;
-    return __fdividef(lr * g, root + eps);
-}
-
 __device__ __forceinline__ void cswap(int& x, int& y) {
     const int lo = x < y ? x : y, hi = x < y ? y : x;
     x = lo; y = hi;

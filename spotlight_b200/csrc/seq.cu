@@ -48,6 +48,8 @@ struct SeqDev {
     float* partial;
     float* loss_out; float* pos_out; float* neg_out;
     float* dE; float* dbias;
+    // fused row-wise optimizer (0 = gradients written to dE / dbias)
+    int32_t opt; float lr, wd, eps; float* sE; float* sbias;
     SegIndex seg;
 };
 
@@ -392,10 +394,32 @@ __global__ void __launch_bounds__(SQ_THREADS) seq_reduce_kernel(SeqDev a) {
                 }
                 b2 += a.gs[t];
             });
-            if (c < D) st4(a.dE + row * D + c, acc);
+            if (c < D) {
+                if (a.opt == SLB_OPT_NONE) {
+                    st4(a.dE + row * D + c, acc);
+                } else if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) {
+                    // row-wise optimizer applied in place: this is the last kernel of the step, every
+                    // gradient that reads E has been formed (SGD / Adagrad change an element only when
+                    // its gradient is non-zero, so this equals the dense update)
+                    const OptV2 o = {a.opt, a.lr, a.wd, a.eps};
+                    float* wrow = const_cast<float*>(a.E) + row * D + c;
+                    float* srow = a.opt == SLB_OPT_ADAGRAD ? a.sE + row * D + c : nullptr;
+                    float4 w4 = ld4(wrow), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (srow) s4 = ld4(srow);
+                    row_update(o, w4, s4, acc);
+                    st4(wrow, w4);
+                    if (srow) st4(srow, s4);
+                }
+            }
             bacc = b2;
         }
-        if (gl == 0) a.dbias[row] = bacc;
+        if (gl == 0) {
+            if (a.opt == SLB_OPT_NONE) a.dbias[row] = bacc;
+            else if (bacc != 0.f) {
+                const OptV2 o = {a.opt, a.lr, a.wd, a.eps};
+                bias_update(o, const_cast<float*>(a.bias) + row, a.opt == SLB_OPT_ADAGRAD ? a.sbias + row : nullptr, bacc);
+            }
+        }
     }
 }
 
@@ -778,7 +802,10 @@ int seq_validate(const slb_seq_step_args* x, bool training) {
         SLB_REQUIRE(x->nonlinearity == 0 || x->nonlinearity == 1, "seq: nonlinearity must be tanh(0) or relu(1)");
     }
     if (training) {
-        SLB_REQUIRE(x->negs && x->bias && x->loss_out && x->dE && x->dbias, "seq: null pointer");
+        SLB_REQUIRE(x->negs && x->bias && x->loss_out, "seq: null pointer");
+        SLB_REQUIRE(x->opt != SLB_OPT_NONE || (x->dE && x->dbias), "seq: dE / dbias needed without a fused optimizer");
+        SLB_REQUIRE(x->opt == SLB_OPT_NONE || x->opt == SLB_OPT_SGD || (x->opt == SLB_OPT_ADAGRAD && x->state_E && x->state_bias),
+                    "seq: fused optimizer is SGD, or Adagrad with state_E / state_bias");
         SLB_REQUIRE(x->loss >= 0 && x->loss <= 3, "seq: bad loss kind");
         SLB_REQUIRE(x->n_neg >= 1 && (x->loss == SLB_LOSS_ADAPTIVE_HINGE || x->n_neg == 1), "seq: bad n_neg");
         if (x->n_layers > 0) SLB_REQUIRE(x->dconv_w && x->dconv_b, "seq: conv grads missing");
@@ -923,6 +950,7 @@ int slb_seq_train_step(const slb_seq_step_args* x, slb_stream_t stream) {
     a.hdr = l.hdr; a.partial = l.partial; a.norm = x->norm_count;
     a.loss_out = x->loss_out; a.pos_out = x->pos_out; a.neg_out = x->neg_out;
     a.dE = x->dE; a.dbias = x->dbias; a.seg = l.seg;
+    a.opt = x->opt; a.lr = x->lr; a.wd = x->weight_decay; a.eps = x->eps; a.sE = x->state_E; a.sbias = x->state_bias;
     SQ_DISPATCH_LPR(lpr, seq_score_kernel, sq_grid((B * T + groups - 1) / groups), st, a);
     SLB_LAUNCH_CHECK("seq_score_kernel");
 

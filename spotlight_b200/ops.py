@@ -633,10 +633,12 @@ def seq_step_args(E, bias, seqs, negs, loss, n_neg, cnn=None, keep=None):
     return a, keep
 
 
-def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False, norm_count=None):
+def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False, norm_count=None, fused=None):
     """Fused forward + backward of one sequence minibatch, dense gradients.
 
-    Returns dict(loss, pos, neg, dE, dbias, dconv_w, dconv_b).
+    Returns dict(loss, pos, neg, dE, dbias, dconv_w, dconv_b).  ``fused`` = dict(kind, lr,
+    weight_decay, eps, state_E, state_bias): the row-wise optimizer is applied to ``E`` / ``bias`` in
+    place inside the step (no dense item-table gradient exists; ``dE`` / ``dbias`` are None).
     """
     require_cuda(E, bias, seqs, negs)
     lib = _lib.load()
@@ -649,14 +651,20 @@ def seq_train_step(E, bias, seqs, negs, loss, n_neg, cnn=None, want_scores=False
         cnn['weights'] = [_f32c(w) for w in cnn['weights']]
         cnn['biases'] = [_f32c(b) for b in cnn['biases']]
     a, keep = seq_step_args(E, bias, seqs, negs, loss, n_neg, cnn)
-    out = dict(loss=torch.empty(1, dtype=torch.float32, device=dev),
-               dE=torch.zeros_like(E), dbias=torch.zeros_like(bias), dconv_w=[], dconv_b=[])
+    out = dict(loss=torch.empty(1, dtype=torch.float32, device=dev), dE=None, dbias=None, dconv_w=[], dconv_b=[])
+    if fused is None:
+        out['dE'], out['dbias'] = torch.zeros_like(E), torch.zeros_like(bias)
     a.loss_out = out['loss'].data_ptr()
     if want_scores:
         out['pos'] = torch.empty((B, S), dtype=torch.float32, device=dev)
         out['neg'] = torch.empty((n_neg * B, S), dtype=torch.float32, device=dev)
         a.pos_out, a.neg_out = out['pos'].data_ptr(), out['neg'].data_ptr()
-    a.dE, a.dbias = out['dE'].data_ptr(), out['dbias'].data_ptr()
+    if fused is None:
+        a.dE, a.dbias = out['dE'].data_ptr(), out['dbias'].data_ptr()
+    else:
+        a.opt, a.lr, a.weight_decay, a.eps = int(fused['kind']), float(fused['lr']), float(fused['weight_decay']), float(fused['eps'])
+        if fused.get('state_E') is not None:
+            a.state_E, a.state_bias = fused['state_E'].data_ptr(), fused['state_bias'].data_ptr()
     if norm_count is not None:
         a.norm_count = norm_count.data_ptr()
     if cnn is not None:

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.optim as optim
 
-from spotlight_b200 import ops
+from spotlight_b200 import _lib, ops
 from spotlight_b200.helpers import _repr_model
 from spotlight_b200.losses import adaptive_hinge_loss, bpr_loss, hinge_loss, pointwise_loss
 from spotlight_b200.rng import SHUFFLE_DEVICE_MAX, shuffled_order_device
@@ -173,9 +173,20 @@ class ImplicitSequenceModel(object):
     def _fused_step(self, batch_sequence, batch_neg, n_neg):
         net = self._net
         spec = net._cnn_spec()
+        fused = None
+        opt = self._optimizer
+        kind = getattr(opt, 'fused_kind', None)
+        if kind in (_lib.OPT_SGD, _lib.OPT_ADAGRAD):
+            # row-wise optimizer inside the step (spotlight_b200.optim): the item table and its bias
+            # are updated in place by the gradient kernel, no dense (num_items, D) gradient exists;
+            # optimizer.step() below then only sees the (tiny) conv parameters
+            hp = opt.fused_hparams()
+            fused = dict(kind=kind, lr=hp['lr'], weight_decay=hp['weight_decay'], eps=hp['eps'],
+                         state_E=opt.fused_state(net.item_embeddings.weight),
+                         state_bias=opt.fused_state(net.item_biases.weight))
         with torch.no_grad():
             out = ops.seq_train_step(net.item_embeddings.weight, net.item_biases.weight,
-                                     batch_sequence, batch_neg, self._loss, n_neg, spec)
+                                     batch_sequence, batch_neg, self._loss, n_neg, spec, fused=fused)
         net.item_embeddings.weight.grad = out['dE']
         net.item_biases.weight.grad = out['dbias']
         if spec is not None:

@@ -109,6 +109,54 @@ def test_seq_step_vs_oracle_sizes(kind, D, S, B):
     assert torch.equal(out['dE'], out2['dE']), 'sequence step is not bit-reproducible'
 
 
+@pytest.mark.parametrize('name,loss', [('pool_bpr', 'bpr'), ('pool_hinge', 'hinge'), ('cnn_pointwise', 'pointwise'),
+                                       ('cnn_pointwise_d128', 'pointwise')])
+def test_seq_step_fused_sgd_golden(name, loss):
+    """The sequence step with the row-wise optimizer fused into the gradient reduction (no dense
+    item-table gradient): one SGD step reproduces E - lr * (the live reference's gradient)."""
+    from spotlight_b200 import _lib, ops
+    g = load_golden(name)
+    spec = _cnn_spec(g) if name.startswith('cnn') else None
+    gE, gb = g['grad.item_embeddings.weight'], g['grad.item_biases.weight']
+    lr = 0.3 / np.abs(gE).max()
+    E, b = t(g['sd.item_embeddings.weight'].copy()), t(g['sd.item_biases.weight'].copy())
+    out = ops.seq_train_step(E, b, t(g['seqs']), t(g['negs']), loss, 1, spec,
+                             fused=dict(kind=_lib.OPT_SGD, lr=lr, weight_decay=0.0, eps=0.0))
+    assert out['dE'] is None and out['dbias'] is None
+    assert_close(out['loss'].item(), g['loss'], 1e-5, what='loss')
+    assert_close(E.cpu().numpy(), g['sd.item_embeddings.weight'].astype(np.float64) - lr * gE, 5e-6, what='E')
+    assert_close(b.cpu().numpy(), g['sd.item_biases.weight'].astype(np.float64) - lr * gb, 5e-6, what='bias')
+    assert float(E[0].abs().sum()) == 0.0                    # the padding row stays frozen
+    if spec is not None:
+        for i in range(len(spec['weights'])):
+            assert_close(out['dconv_w'][i].cpu().numpy(), g['grad.cnn_%d.weight' % i], 1e-5, what='dW%d' % i)
+
+
+@pytest.mark.parametrize('name,loss,rep', [('fit_pool_hinge', 'hinge', 'pooling'),
+                                           ('fit_cnn_pointwise', 'pointwise', 'cnn')])
+def test_sequence_model_fit_golden_fused_optimizer(name, loss, rep, capsys):
+    """ImplicitSequenceModel.fit with spotlight_b200.optim.fused_sgd (item table updated inside the
+    step, conv parameters by the optimizer's own step()) against the reference trajectory."""
+    from spotlight_b200 import optim
+    from spotlight_b200.interactions import SequenceInteractions
+    from spotlight_b200.sequence.implicit import ImplicitSequenceModel
+    g = load_golden(name)
+    inter = SequenceInteractions(g['seqs'], num_items=int(g['num_items']))
+    model = ImplicitSequenceModel(loss=loss, representation=rep, embedding_dim=int(g['dim']),
+                                  batch_size=int(g['batch']), n_iter=int(g['n_iter']),
+                                  optimizer_func=optim.fused_sgd(lr=0.5), use_cuda=True,
+                                  random_state=np.random.RandomState(int(g['seed'])))
+    model._initialize(inter)
+    model._net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('init.')})
+    model.fit(inter, verbose=True)
+    lines = [l for l in capsys.readouterr().out.strip().split('\n') if l.startswith('Epoch')]
+    losses = np.array([float(l.split('loss')[1]) for l in lines])
+    assert_close(losses, g['epoch_losses'], 1e-5, what='epoch losses')
+    for k, v in model._net.state_dict().items():
+        assert_close(v.cpu().numpy(), g['final.' + k], 1e-4, atol=1e-7, what=k)
+    assert model._net.item_embeddings.weight.grad is None
+
+
 @pytest.mark.parametrize('name,loss,rep', [('fit_pool_hinge', 'hinge', 'pooling'),
                                            ('fit_cnn_pointwise', 'pointwise', 'cnn')])
 def test_sequence_model_fit_golden(name, loss, rep, capsys):
