@@ -136,11 +136,37 @@ class ClockSampler(object):
                 pass
             time.sleep(self.period)
 
+    def nvlink_kib(self):
+        """Cumulative NVLink payload counters of this GPU (KiB transmitted, KiB received), summed
+        over its links, from the driver's hardware counters (NVML field values); None if absent."""
+        if self._h is None:
+            return None
+        nv = self._nv
+        try:
+            vals = nv.nvmlDeviceGetFieldValues(self._h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                         (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+            out = []
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    return None
+                out.append(int(v.value.ullVal))
+            return tuple(out)
+        except Exception:
+            return None
+
     def mark_begin(self):
+        self.nv0 = self.nvlink_kib()
         self.t0 = time.perf_counter()
 
     def mark_end(self):
         self.t1 = time.perf_counter()
+        self.nv1 = self.nvlink_kib()
+
+    def nvlink_delta_bytes(self):
+        a, b = getattr(self, 'nv0', None), getattr(self, 'nv1', None)
+        if not a or not b:
+            return None
+        return {'tx_bytes': (b[0] - a[0]) * 1024, 'rx_bytes': (b[1] - a[1]) * 1024}
 
     def stop(self):
         self._stop.set()
@@ -452,6 +478,12 @@ def main_sharded(a, rank, world, local):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     clocks = sampler.stop() if sampler else None
+    hw_nv = None
+    if sampler:
+        d = sampler.nvlink_delta_bytes()
+        if d:
+            hw_nv = dict(d, tx_gbs=d['tx_bytes'] / (ms * 1e-3) / 1e9, rx_gbs=d['rx_bytes'] / (ms * 1e-3) / 1e9,
+                         note='counter window = the timed region (host marks around it)')
 
     # ---- end to end through the public multi-GPU API (host ids) ---------
     e2e = None
@@ -486,7 +518,11 @@ def main_sharded(a, rank, world, local):
                 'nvlink': {'exchange_gbytes_per_rank': a2a_gb,
                            'achieved_gbs_per_rank': a2a_gb / (ms * 1e-3),
                            'rows_requested_per_step': stats['rows_requested'] / K,
-                           'source': 'bytes counted from the tensors handed to NCCL / timed region'},
+                           'source': 'bytes counted from the tensors handed to NCCL / timed region',
+                           # the same window through the GPU's NVLink hardware counters (NVML field
+                           # values NVLINK_THROUGHPUT_DATA_TX / RX of rank 0's GPU, all links)
+                           'hw_counters': hw_nv,
+                           'peak_gbs_per_direction': 900.0},
                 'roofline': None, 'cpu_baseline': None}
         print(json.dumps(line))
     dist.destroy_process_group()

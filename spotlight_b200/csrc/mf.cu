@@ -919,8 +919,17 @@ __global__ void __launch_bounds__(MF_THREADS) mf_fwd_bloom_kernel(MfDev a, const
             gp *= invB; gn *= invB;
             if (bad) { gp = 0.f; gn = 0.f; }
             if (a.pos_out) a.pos_out[bb] = p;
-            h.ids_u2[bb] = u; h.g_u2[bb] = gp;
-            h.ids_u2[a.B + bb] = nuid; h.g_u2[a.B + bb] = gn;
+            // user-bias gradient: when the negative is scored with the same user (every loss but
+            // adaptive hinge) the two halves are emitted as ONE pair, so that bpr / hinge's
+            // gp + gn = 0 is an exact zero (dropped downstream) and not a rounding residue of two
+            // sums that Adagrad would turn into a full step
+            if (nuid == u) {
+                h.ids_u2[bb] = u; h.g_u2[bb] = gp + gn;
+                h.ids_u2[a.B + bb] = u; h.g_u2[a.B + bb] = 0.f;
+            } else {
+                h.ids_u2[bb] = u; h.g_u2[bb] = gp;
+                h.ids_u2[a.B + bb] = nuid; h.g_u2[a.B + bb] = gn;
+            }
             h.ids_i2[bb] = i; h.g_i2[bb] = gp;
             h.ids_i2[a.B + bb] = njid; h.g_i2[a.B + bb] = gn;
             const int64_t t0 = bb * 2 * pairs;
