@@ -26,9 +26,16 @@ for name, spec in (('pool', None),
                    ('cnn_k3', dict(kernel_width=[3], dilation=[1], nonlinearity='tanh', residual=True,
                                    weights=[torch.randn(D, D, 3, 1, device=dev) * 0.05],
                                    biases=[torch.zeros(D, device=dev)]))):
+    from spotlight_b200 import _lib
+    sE, sb = torch.zeros_like(E), torch.zeros_like(bias)
+    fused = None if os.environ.get('SEQ_DENSE') else dict(kind=_lib.OPT_ADAGRAD, lr=0.05, weight_decay=0.0, eps=1e-10,
+                                                       state_E=sE, state_bias=sb)
+
     def step(k):
+        # default: row-wise Adagrad fused into the step (no dense 512 MB item-table gradient);
+        # SEQ_DENSE=1: the round-1 measurement (dense dE / dbias, no optimizer)
         sl = slice(k * B, (k + 1) * B)
-        return ops.seq_train_step(E, bias, seqs[sl], negs[sl], 'pointwise', 1, spec)
+        return ops.seq_train_step(E, bias, seqs[sl], negs[sl], 'pointwise', 1, spec, fused=fused)
     for k in range(3):
         step(k)
     torch.cuda.synchronize()
