@@ -211,6 +211,9 @@ class GpuBackend(object):
                 out['dconv_w'], out['dconv_b'])
 
 
+_CHUNK_VALUES = 24 << 20        # negatives per sampler chunk: within the one-round reach of the jump table
+
+
 class _GpuEpochSampler(object):
     def __init__(self, device, num_items, random_state, total):
         from spotlight_b200 import rng
@@ -683,7 +686,7 @@ class ShardedImplicitFactorizationModel(object):
                 raise ValueError('Degenerate epoch loss: {}'.format(epoch_loss))
         return self
 
-    def _run_epoch_device(self, u, i, chunk_batches=16):
+    def _run_epoch_device(self, u, i):
         """One epoch over the (already shuffled) global ids ``u`` / ``i``, held identically on
         every rank's device: global negative stream (chunked, on a side stream where the
         backend has one), owner partition, and the sharded steps of this rank's members.
@@ -706,7 +709,7 @@ class ShardedImplicitFactorizationModel(object):
                    if hasattr(be, 'epoch_sampler') else _HostEpochSampler(be, self._num_items, self._random_state))
         nsteps = len(bounds) - 1
         losses = []
-        k, cur = 0, 1
+        k, cur = 0, max(1, _CHUNK_VALUES // (B * nn))
         while k < nsteps:
             # one draw per chunk of global minibatches; a minibatch draws len(batch) * n values at
             # once (implicit.py:256-259, 266-275): the n-block of the member at epoch position p
@@ -725,7 +728,7 @@ class ShardedImplicitFactorizationModel(object):
                 else:
                     losses.append(self.mf.step(mu[sl], mi[sl], mn, self._loss, min(B, n - kk * B),
                                                self._exchange))
-            k, cur = hi_k, min(2 * cur, chunk_batches)
+            k = hi_k
         sampler.finish()
         return float(torch.stack(losses).mean()) if losses else 0.0
 
@@ -736,7 +739,7 @@ class ShardedImplicitFactorizationModel(object):
             cache[key] = make()
         return cache[key]
 
-    def _epoch_dense_gpu(self, u, i, mine, bounds, chunk_batches=16):
+    def _epoch_dense_gpu(self, u, i, mine, bounds):
         """Whole-shard exchange epoch on the product kernels with nothing but launches on the
         host side of the loop: per global minibatch k
 
@@ -771,13 +774,19 @@ class ShardedImplicitFactorizationModel(object):
         assert fws.numel() > 0, 'planned step unavailable for dim %d' % D
         losses = torch.zeros(nsteps, dtype=torch.float32, device=dev)
         sampler = be.epoch_sampler(self._num_items, self._random_state, n)
+        # The whole stream is enqueued up front in chunks as large as one jump round reaches
+        # (~24 M values): a chunk costs one latency-bound jump round + one fill round whatever its
+        # size, and that generator slows down several-fold when it shares SMs with the training
+        # kernels -- so as much as possible is drawn before the first step (measured at N = 4: the
+        # 1, 2, 4, 8-batch doubling schedule stalled 20 steps for 27 ms in total).
         waits = []                                             # (first step, event) per chunk of negatives
-        k, cur = 0, 1
+        per = max(1, _CHUNK_VALUES // B)
+        k = 0
         while k < nsteps:
-            hi_k = min(k + cur, nsteps)
+            hi_k = min(k + per, nsteps)
             _, ev = sampler.draw(min(hi_k * B, n) - k * B)
             waits.append((k, ev))
-            k, cur = hi_k, min(2 * cur, chunk_batches)
+            k = hi_k
         negs_all = sampler.out
         plan_ev = [torch.cuda.Event(), torch.cuda.Event()]
         done_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -819,27 +828,57 @@ class ShardedImplicitFactorizationModel(object):
                                                             ops._stream()), 'plan')
                 plan_ev[slot].record(pstream)
 
+        import os
+        import time
+        trace = bool(os.environ.get('SLB_TRACE_STEP'))      # diagnostics: device time per phase (events), host time per step
+        marks, host_t = [], []
+
+        def mark():
+            if trace:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(main)
+                marks.append(e)
+
         prep(0)
         for k in range(nsteps):
+            t_host = time.perf_counter()
             if k + 1 < nsteps:
                 prep(k + 1)
             slot = k & 1
             m = bounds[k + 1] - bounds[k]
+            mark()
             dist.all_gather_into_tensor(buf['full_W'], st.Wi, group=self.mf.group)
             dist.all_gather_into_tensor(buf['full_b'], st.bi, group=self.mf.group)
+            mark()
             buf['dW'].zero_()
             buf['db'].zero_()
             main.wait_event(plan_ev[slot])
+            mark()
             if m:
                 _lib.check(lib.slb_mf_train_step_phases(ctypes.byref(args[slot]), 6 | (slot << 8),
                                                         ops._stream()), 'step')
             done_ev[slot].record(main)
+            mark()
             dist.reduce_scatter_tensor(buf['gW'], buf['dW'], group=self.mf.group)
             dist.reduce_scatter_tensor(buf['gb'], buf['db'], group=self.mf.group)
+            mark()
             _lib.check(lib.slb_adagrad_dense(ops._ptr(st.Wi), ops._ptr(st.sWi), ops._ptr(buf['gW']), chunk * D,
                                              st.lr, st.eps, ops._stream()), 'adagrad')
             _lib.check(lib.slb_adagrad_dense(ops._ptr(st.bi), ops._ptr(st.sbi), ops._ptr(buf['gb']), chunk,
                                              st.lr, st.eps, ops._stream()), 'adagrad')
+            mark()
+            host_t.append(time.perf_counter() - t_host)
+        if trace and self.rank == 0 and nsteps > 4:
+            torch.cuda.synchronize()
+            names = ['all_gather', 'zero+wait_plan', 'user+item', 'reduce_scatter', 'adagrad', 'gap_to_next']
+            acc = [0.0] * 6
+            for k in range(2, nsteps - 1):
+                ev = marks[6 * k:6 * k + 7]
+                for j in range(6):
+                    acc[j] += ev[j].elapsed_time(ev[j + 1])
+            print('[trace-step] world %d device ms per step:' % self.world,
+                  {nm: round(v / (nsteps - 3), 4) for nm, v in zip(names, acc)},
+                  'host ms per step %.3f' % (1e3 * sum(host_t[2:]) / len(host_t[2:])), flush=True)
             self.mf.stats['bytes_a2a'] += 2 * (buf['full_W'].numel() + buf['full_b'].numel()) * 4
             self.mf.stats['rows_requested'] += P * chunk
         pstream.wait_stream(main)                              # later plan-stream work follows this epoch
