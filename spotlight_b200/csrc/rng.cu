@@ -113,6 +113,12 @@ __device__ __forceinline__ void mt_jump_apply(const uint32_t* __restrict__ in, c
     __syncthreads();
     if (t < 32) E[MT_N + t] = mt_mix(E[t], E[t + 1], E[t + MT_M]);
     __syncthreads();
+    // thread t only ever reads E[t .. t + 31] (the same window for every coefficient word): keep
+    // it in registers, so the XOR phase of an iteration is 32 register operations and no
+    // shared-memory traffic (the loop was bound by 32 predicated shared loads per thread)
+    uint32_t e[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) e[b] = t < MT_N ? E[t + b] : 0u;
     int o = 0;                                  // circular base of acc
     for (int w = MT_N - 1; w >= 0; --w) {
         const uint32_t cw = __ldg(poly + w);
@@ -130,8 +136,7 @@ __device__ __forceinline__ void mt_jump_apply(const uint32_t* __restrict__ in, c
         if (cw != 0u && t < MT_N) {
             uint32_t v = 0;
 #pragma unroll
-            for (int b = 0; b < 32; ++b)
-                if ((cw >> b) & 1u) v ^= E[t + b];
+            for (int b = 0; b < 32; ++b) v ^= e[b] & (0u - ((cw >> b) & 1u));
             int i = o + t; if (i >= MT_N) i -= MT_N;
             acc[i] ^= v;
         }

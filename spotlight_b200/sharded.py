@@ -696,7 +696,8 @@ class ShardedImplicitFactorizationModel(object):
         if n == 0:
             return 0.0
         # this rank's members of every minibatch, in minibatch order (no dependence on negatives)
-        mine = torch.nonzero(torch.div(u, plan.uchunk, rounding_mode='floor') == self.rank).reshape(-1)
+        ulo, uhi = plan.user_range(self.rank)
+        mine = torch.nonzero((u >= ulo) & (u < uhi)).reshape(-1)
         edges = torch.arange(0, n + B, B, device=mine.device).clamp_(max=n)
         bounds = torch.searchsorted(mine, edges).tolist()                   # the epoch's one sync
         dense = self._exchange == 'dense' or (self._exchange == 'auto' and
