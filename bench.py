@@ -472,6 +472,9 @@ def main_sharded(a, rank, world, local):
         _rng.reserve(a.items, K * gB, dev)
         _prime2 = torch.empty(16 * K * gB, dtype=torch.uint8, device=dev)
     del _prime, _prime2
+    import gc
+    gc.collect()
+    gc.disable()            # no collector pause inside a 10-30 ms timed region (re-enabled right after)
     dist.barrier()
     torch.cuda.synchronize()
     if sampler:
@@ -483,6 +486,7 @@ def main_sharded(a, rank, world, local):
     e1.record()
     dist.barrier()
     torch.cuda.synchronize()
+    gc.enable()
     if sampler:
         sampler.mark_end()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -570,6 +574,9 @@ def main_ours(a):
     with torch.cuda.stream(_side_stream(dev)):
         _rng.reserve(a.items, min(64, K) * B, dev)
     del _prime
+    import gc
+    gc.collect()
+    gc.disable()            # no collector pause inside the timed region (re-enabled right after)
     barrier()
     if sampler:
         sampler.mark_begin()
@@ -578,6 +585,7 @@ def main_ours(a):
     epoch_loss = model._run_epoch_device(users[W * B:], items[W * B:])  # exactly K steps
     e1.record()
     barrier()
+    gc.enable()
     if sampler:
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
