@@ -5,8 +5,10 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 A *step* is one minibatch through the fit() hot path: negative draw (device
-MT19937, bit-exact with NumPy), fused forward kernel, segment-index build,
-deterministic backward kernel, fused row-wise Adagrad update.
+MT19937, bit-exact with NumPy), the integer plan of the minibatch (row index of
+both tables, on its own stream), mf_user_kernel (forward + user-row gradient +
+in-place row-wise Adagrad) and mf_item_kernel (item-row gradient + update):
+csrc/mf_v2.cuh, deterministic (no float atomics).
 
 One JSON line on stdout (rank 0):
   value      whole-job interactions/s with ids resident in HBM (device timed,
@@ -680,7 +682,7 @@ def main_ours(a):
         r = run_cpu_port(a, a.cpu_steps, 2)
         cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
-    n_chunks = 7 + max(0, (K - 127 + 63) // 64)      # sampler chunks: 1,2,4,..,64 batches
+    n_chunks = (K + 47) // 48                        # sampler chunks of up to 48 batches
     per_step = 10 if 'mf_user' in kb else 10         # planned: 6 plan + 2 user + 2 item; first generation: 10
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',

@@ -1080,6 +1080,11 @@ int validate(const slb_mf_step_args* x) {
         SLB_REQUIRE(x->state_Wu && x->state_bu, "mf_train_step: adagrad needs state");
         SLB_REQUIRE(x->opt_users_only || (x->state_Wi && x->state_bi), "mf_train_step: adagrad needs item state");
     }
+#if defined(BWD_OPT_CT)
+    // experiment build: the first-generation user-side kernel folds this optimizer and zero decay in
+    SLB_REQUIRE(x->opt == SLB_OPT_NONE || (x->opt == BWD_OPT_CT && x->weight_decay == 0.f),
+                "mf_train_step: this build was compiled with -DBWD_OPT_CT=%d and weight_decay 0", BWD_OPT_CT);
+#endif
     const size_t need = slb_mf_step_workspace_bytes(x->batch, x->n_neg, x->loss, x->num_users, x->num_items);
     if (x->workspace_bytes < need) {
         slb_set_error("mf_train_step: workspace too small (%zu < %zu)", x->workspace_bytes, need);

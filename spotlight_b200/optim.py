@@ -42,7 +42,12 @@ class FusedSGD(torch.optim.SGD):
 class FusedAdagrad(torch.optim.Adagrad):
     """Adagrad with ``lr_decay = 0`` and ``initial_accumulator_value = 0``
     (torch defaults).  State lives in ``self.state[p]['sum']`` exactly as in
-    ``torch.optim.Adagrad`` so training can continue with either."""
+    ``torch.optim.Adagrad`` so training can continue with either.
+
+    ``weight_decay``: on the fused epoch pipeline it is added (as ``wd * w``) to the gradient
+    of the rows a minibatch touches with a non-zero gradient only; torch's dense Adagrad decays
+    every row on every step.  With ``weight_decay = 0`` (the default, and what the parity tests
+    use) the two are the same update; with ``weight_decay > 0`` they differ."""
 
     fused_kind = _lib.OPT_ADAGRAD
 
@@ -138,6 +143,8 @@ class FusedAdam(torch.optim.Optimizer):
         if len(emb) != len(bias) or any(W.shape[0] != b.shape[0] for W, b in zip(emb, bias)):
             raise RuntimeError('FusedAdam.flush: expected (embedding, bias) table pairs')
         for W, b in zip(emb, bias):
+            if not W.is_cuda:
+                continue        # CPU tensors only ever see the dense step() below, which leaves every row current
             rows = W.shape[0]
             m, v, last = self.fused_states(W)
             bm, bv, _ = self.fused_states(b)

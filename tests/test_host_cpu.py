@@ -180,3 +180,32 @@ def test_every_entry_point_is_documented():
                     not (name.endswith('_workspace_bytes') and
                          any(name == p + 'workspace_bytes' for p in prefixes))]
     assert not undocumented, undocumented
+
+
+def test_fused_adam_schedule_and_dense_fallback():
+    """FusedAdam (row-wise lazy-exact Adam, the reference's default optimizer at O(batch)): the
+    per-step scalar table the kernels replay with, and the dense step() fallback, against
+    torch.optim.Adam on CPU tensors (implicit.py:143-148)."""
+    import numpy as np
+    import torch
+    from spotlight_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    W1 = torch.nn.Parameter(torch.randn(7, 4))
+    b1 = torch.nn.Parameter(torch.randn(7, 1))
+    W2 = torch.nn.Parameter(W1.detach().clone())
+    b2 = torch.nn.Parameter(b1.detach().clone())
+    mine = FusedAdam([W1, b1], lr=1e-2, weight_decay=1e-3)
+    ref = torch.optim.Adam([W2, b2], lr=1e-2, weight_decay=1e-3)
+    sched = mine.schedule(10, torch.device('cpu')).reshape(-1, 2).numpy()
+    for t in (1, 2, 7, 10):
+        assert abs(sched[t, 0] - 1e-2 / (1 - 0.9 ** t)) < 1e-7 * sched[t, 0] + 1e-12
+        assert abs(sched[t, 1] - np.sqrt(1 - 0.999 ** t)) < 1e-6
+    for _ in range(5):
+        g, gb = torch.randn(7, 4), torch.randn(7, 1)
+        W1.grad, b1.grad, W2.grad, b2.grad = g.clone(), gb.clone(), g.clone(), gb.clone()
+        mine.step()
+        ref.step()
+    assert mine.steps_taken == 5
+    assert torch.allclose(W1, W2, rtol=1e-5, atol=1e-7) and torch.allclose(b1, b2, rtol=1e-5, atol=1e-7)
+    assert int(mine.state[W1]['last'].min()) == 5
+
