@@ -13,6 +13,8 @@ Contents (every function cites the reference file:line it restates):
 * ``mf``        -- BilinearNet forward / the four losses / closed-form backward.
 * ``seq``       -- PoolNet and CNNNet forward / backward closed forms.
 * ``shuffle``   -- ``RandomState.shuffle`` (Fisher-Yates on the same stream).
+* ``adam``      -- the row-wise lazy-exact Adam scheme (catch-up before the forward, real step,
+                   flush), pinned against the reference's recorded default-Adam trajectory.
 * ``torch_port``-- the reference's fit() loop restated on stock torch CPU ops
                    (the timed ``cpu_baseline`` "port", used by bench.py only when
                    the unmodified reference is not installed under
