@@ -83,6 +83,23 @@ class GpuBackend(object):
         host = counts.tolist()                       # the step's one bucketing sync
         return uniq[:host[nparts + 1]], inverse, host[:nparts + 1]
 
+    def unique_bucket_dev(self, ids, rows, chunk, nparts):
+        """As unique_bucket, with nothing read back: (uniq [min(n, rows)] of which the first
+        counts[nparts + 1] entries are valid, inverse, counts = per-owner boundaries + unique count,
+        all on the device)."""
+        lib = _lib.load()
+        ids = ids.contiguous()
+        n = ids.numel()
+        uniq = torch.empty(min(n, rows), dtype=torch.int64, device=ids.device)
+        inverse = torch.empty(n, dtype=torch.int64, device=ids.device)
+        counts = torch.empty(nparts + 2, dtype=torch.int64, device=ids.device)
+        ws = ops.workspace('uq%d' % rows, lib.slb_unique_workspace_bytes(n, rows), ids.device)
+        rc = lib.slb_unique_bucket(ops._ptr(ids), n, rows, chunk, nparts, ops._ptr(uniq),
+                                   ops._ptr(inverse), ops._ptr(counts), ops._ptr(ws), ws.numel(),
+                                   ops._stream())
+        _lib.check(rc, 'unique_bucket')
+        return uniq, inverse, counts
+
     def gather(self, W, b, local_ids):
         rows = ops.embedding(W, local_ids, [], -1)
         bias = ops.embedding(b.reshape(-1, 1), local_ids, [], -1).reshape(-1)
@@ -344,6 +361,8 @@ class ShardedMF(object):
         if exchange == 'dense' or (exchange == 'auto' and
                                    self._dense_exchange_pays(global_batch // self.plan.world)):
             return self.step_dense(users, items, negs, loss, global_batch, n_neg)
+        if exchange == 'a2a_fixed':
+            return self.step_a2a_fixed(users, items, negs, loss, global_batch, getattr(self, 'fixed_slots', None))
         return self.step_a2a(users, items, negs, loss, global_batch, n_neg)
 
     def step_dense(self, users, items, negs, loss, global_batch, n_neg=1):
@@ -446,6 +465,73 @@ class ShardedMF(object):
         else:
             loss_share, g_rows, g_bias = st.bi.new_zeros(()), cache_rows[:0], cache_bias[:0]
         self._return_grads(route, g_rows, g_bias)
+        return self._global_loss(loss_share)
+
+    def step_a2a_fixed(self, users, items, negs, loss, global_batch, slots=None):
+        """Per-row routing WITHOUT host synchronisation: every rank sends every peer a fixed
+        number of request slots (``slots`` per peer; unused slots carry -1), so the all-to-alls
+        have equal, host-known splits and the bucket sizes never leave the device.  Traffic is
+        padded to the slot capacity; a bucket that does not fit raises ``self.overflow`` (a device
+        flag the caller reads once per epoch -- the step's result is then invalid and the epoch
+        must be rerun with more slots or the synchronising ``step_a2a``).
+
+        CPU-verified against the float64 oracle (tests/test_sharded_cpu.py, gloo); NOT yet run or
+        measured on the B200s -- the round's GPU budget was spent."""
+        plan, st, P, be = self.plan, self.st, self.plan.world, self.backend
+        dev = users.device
+        B = users.numel()
+        ids = torch.cat([items, negs])
+        n = ids.numel()
+        C = int(slots or min(plan.ichunk, (3 * max(n, 1)) // (2 * P) + 1024))
+        D = st.Wi.shape[1]
+        if not hasattr(self, 'overflow'):
+            self.overflow = torch.zeros((), dtype=torch.int64, device=dev)
+        if n:
+            uniq, inverse, counts = be.unique_bucket_dev(ids, plan.num_items, plan.ichunk, P)
+            cap = uniq.numel()
+            pos = torch.arange(cap, device=dev)
+            valid = pos < counts[P + 1]
+            owner = torch.where(valid, torch.div(uniq, plan.ichunk, rounding_mode='floor'), torch.zeros_like(uniq))
+            owner = owner.clamp_(0, P - 1)
+            rel = pos - counts[:P + 1][owner]
+            ok = valid & (rel < C) & (rel >= 0)
+            self.overflow += (valid & ~ok).sum()
+            slot = torch.where(ok, owner * C + rel, torch.full_like(rel, P * C))      # P*C = a dump slot
+            req = torch.full((P * C + 1,), -1, dtype=torch.int64, device=dev)
+            req[slot] = torch.where(ok, uniq, torch.full_like(uniq, -1))
+            req = req[:P * C].contiguous()
+        else:
+            cap, inverse = 0, ids
+            req = torch.full((P * C,), -1, dtype=torch.int64, device=dev)
+        got = torch.empty_like(req)
+        dist.all_to_all_single(got, req, group=self.group)
+        live = got >= 0
+        local = torch.where(live, got - st.ilo, torch.zeros_like(got))
+        rows, bias = be.gather(st.Wi, st.bi, local)
+        back_rows, back_bias = torch.empty_like(rows), torch.empty_like(bias)
+        dist.all_to_all_single(back_rows, rows.contiguous(), group=self.group)
+        dist.all_to_all_single(back_bias, bias.contiguous(), group=self.group)
+        self.stats['bytes_a2a'] += 2 * (rows.numel() + bias.numel()) * 4 + 8 * req.numel()
+        if B:
+            take = slot.clamp(max=P * C - 1)
+            okf = ok.to(back_rows.dtype)
+            cache_rows = back_rows[take] * okf[:, None]
+            cache_bias = back_bias[take] * okf
+            loss_share, g_rows, g_bias = be.local_step(st, cache_rows, cache_bias, cap, users - st.ulo,
+                                                       inverse[:B], inverse[B:], loss, global_batch, 1)
+            send_g = g_rows.new_zeros((P * C + 1, D))
+            send_gb = g_bias.new_zeros(P * C + 1)
+            send_g[slot] = g_rows * okf[:, None]
+            send_gb[slot] = g_bias * okf
+            send_g, send_gb = send_g[:P * C].contiguous(), send_gb[:P * C].contiguous()
+        else:
+            loss_share = st.bi.new_zeros(())
+            send_g, send_gb = st.Wi.new_zeros((P * C, D)), st.bi.new_zeros(P * C)
+        g_recv, gb_recv = torch.empty_like(send_g), torch.empty_like(send_gb)
+        dist.all_to_all_single(g_recv, send_g, group=self.group)
+        dist.all_to_all_single(gb_recv, send_gb, group=self.group)
+        # unused slots carry local row 0 with a zero gradient: they add nothing
+        be.owner_update(st, local, g_recv, gb_recv)
         return self._global_loss(loss_share)
 
     def step_adaptive(self, users, items, negs_block, bpos, batch_users, n_neg):

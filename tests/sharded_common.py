@@ -19,6 +19,12 @@ class NumpyBackend(object):
         bounds = [int(np.searchsorted(uniq, p * chunk)) for p in range(nparts)] + [len(uniq)]
         return torch.from_numpy(uniq), torch.from_numpy(inverse.astype(np.int64)), bounds
 
+    def unique_bucket_dev(self, ids, rows, chunk, nparts):
+        uniq, inverse, bounds = self.unique_bucket(ids, rows, chunk, nparts)
+        pad = torch.full((min(ids.numel(), rows),), 123456789, dtype=torch.int64)     # garbage beyond the count
+        pad[:uniq.numel()] = uniq
+        return pad, inverse, torch.tensor(bounds + [uniq.numel()], dtype=torch.int64)
+
     def gather(self, W, b, local_ids):
         i = local_ids.numpy()
         return torch.from_numpy(W.numpy()[i].copy()), torch.from_numpy(b.numpy()[i].copy())
@@ -175,7 +181,7 @@ def oracle_run(params, batches, loss, lr, eps=1e-10, n_neg=1):
 
 
 def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_capacity=None,
-                exchange='a2a'):
+                exchange='a2a', fixed_slots=None):
     """Runs the steps on this rank; returns (all-gathered full tables, losses)."""
     from spotlight_b200.sharded import ShardedMF, ShardPlan, ShardState
     U, D = params[0].shape
@@ -183,6 +189,7 @@ def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_c
     plan = ShardPlan(U, I, world)
     st = ShardState(plan, rank, D, device, lr=lr, init=[torch.from_numpy(p) for p in params])
     model = ShardedMF(plan, st, rank, backend, cache_capacity=cache_capacity)
+    model.fixed_slots = fixed_slots
     losses = []
     for users, items, negs in batches:
         mine = plan.user_owner(users) == rank
@@ -196,7 +203,8 @@ def sharded_run(rank, world, params, batches, loss, lr, device, backend, cache_c
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
         out.append(torch.cat(parts)[:n].cpu().numpy())
-    return out, losses, model.stats
+    stats = dict(model.stats, overflow=int(getattr(model, 'overflow', 0)))
+    return out, losses, stats
 
 
 def make_seq_problem(seed, I, D, B, S, steps, layers=0, k=3):

@@ -23,7 +23,7 @@ from conftest import ROOT, assert_close
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def _worker(rank, world, port, loss, q, exchange='a2a'):
+def _worker(rank, world, port, loss, q, exchange='a2a', fixed_slots=None):
     import sharded_common as sc
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -31,7 +31,7 @@ def _worker(rank, world, port, loss, q, exchange='a2a'):
     try:
         params, batches = sc.make_problem(5, 101, 57, 8, 96, 3)
         got, losses, stats = sc.sharded_run(rank, world, params, batches, loss, 0.05, 'cpu',
-                                            sc.NumpyBackend(), exchange=exchange)
+                                            sc.NumpyBackend(), exchange=exchange, fixed_slots=fixed_slots)
         if rank == 0:
             q.put((got, losses, stats))
     finally:
@@ -40,7 +40,8 @@ def _worker(rank, world, port, loss, q, exchange='a2a'):
 
 @pytest.mark.parametrize('world,loss,exchange', [(2, 'bpr', 'a2a'), (3, 'bpr', 'a2a'),
                                                  (2, 'pointwise', 'a2a'), (2, 'bpr', 'dense'),
-                                                 (3, 'pointwise', 'dense')])
+                                                 (3, 'pointwise', 'dense'), (2, 'bpr', 'a2a_fixed'),
+                                                 (3, 'pointwise', 'a2a_fixed')])
 def test_sharded_step_matches_single_process(world, loss, exchange):
     import sharded_common as sc
     ctx = mp.get_context('spawn')
@@ -61,6 +62,24 @@ def test_sharded_step_matches_single_process(world, loss, exchange):
     # each distinct row crosses the wire once per rank per step, never per use
     if exchange == 'a2a':
         assert stats['rows_requested'] <= 3 * 57
+    if exchange == 'a2a_fixed':
+        assert stats['overflow'] == 0
+
+
+def test_fixed_slot_exchange_reports_overflow():
+    """Too few request slots per peer: the no-sync exchange must say so (device flag), not
+    silently train on a truncated row cache."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 26500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 'bpr', q, 'a2a_fixed', 3)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, losses, stats = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert stats['overflow'] > 0
 
 
 _CNN = dict(kernel_width=[3, 3], dilation=[1, 2], nonlinearity='tanh', residual=True)
