@@ -293,8 +293,10 @@ def main_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 12))       # each reference step is O(table + batch): seconds
-    warm = max(1, min(a.warmup, 3))
+    # each reference step is O(table + batch) (about a second at the default batch on the box's
+    # host cores): K and W are honoured up to a bound that keeps the arm within a few minutes
+    steps = max(1, min(a.steps, 60))
+    warm = max(1, min(a.warmup, 5))
     r = run_cpu_port(a, steps, warm)
     line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
             'n_gpus': a.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],

@@ -209,3 +209,28 @@ def test_fused_adam_schedule_and_dense_fallback():
     assert torch.allclose(W1, W2, rtol=1e-5, atol=1e-7) and torch.allclose(b1, b2, rtol=1e-5, atol=1e-7)
     assert int(mine.state[W1]['last'].min()) == 5
 
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times beside ours): runs the
+    reference's own fit loop (baseline/_ref when installed, else the oracle port) on the
+    host cores and prints one JSON line with the contract's keys.  Tiny workload here."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1',
+           '--batch', '2048', '--users', '5000', '--items', '2000', '--dim', '16']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and 'unavailable' not in line
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['steps'] == 2 and line['warmup'] == 1 and line['n_gpus'] == 1
+    assert line['value'] > 0 and line['higher_is_better'] is True
+    cb = line['cpu_baseline']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == line['value']
+    assert line['e2e']['value'] == line['value']
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
