@@ -39,6 +39,12 @@ def require_cuda(*tensors):
             raise RuntimeError(
                 'spotlight_b200 ops need CUDA tensors (sm_100a); there is no CPU path. '
                 'Construct the model with use_cuda=True.')
+        if t is not None and t.device.index != torch.cuda.current_device():
+            # the library launches on the current device and never calls cudaSetDevice
+            raise RuntimeError(
+                'spotlight_b200 ops launch on the current CUDA device (cuda:%d) but were given a tensor '
+                'on %s; call torch.cuda.set_device(...) first (one process per GPU).'
+                % (torch.cuda.current_device(), t.device))
 
 
 def _f32c(t: Tensor) -> Tensor:
