@@ -874,6 +874,12 @@ class ShardedImplicitFactorizationModel(object):
             _, ev = sampler.draw(min(hi_k * B, n) - k * B)
             waits.append((k, ev))
             k = hi_k
+        import os
+        if os.environ.get('SLB_SAMPLER_UPFRONT'):
+            # experiment switch: every chunk becomes a dependency of step 0,
+            # i.e. the whole epoch's negatives are drawn before the first step and nothing of the
+            # generator overlaps the training kernels
+            waits = [(0, ev) for _, ev in waits]
         negs_all = sampler.out
         plan_ev = [torch.cuda.Event(), torch.cuda.Event()]
         done_ev = [torch.cuda.Event(), torch.cuda.Event()]
